@@ -1,0 +1,5 @@
+"""oracle/ -- CPU restatements of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import anything from here.  graphgan_b200/ (the product) never does.
+"""
