@@ -1,0 +1,77 @@
+// adam.cu -- K3: TF1.8 AdamOptimizer "sparse" apply, which is dense (sm_100a).
+//
+// generator.py:30-31 / discriminator.py:31-32 call tf.train.AdamOptimizer(lr).minimize(loss)
+// on variables whose gradients are IndexedSlices.  TF 1.8's _apply_sparse_shared does
+//     m <- m * beta1;  m[idx] += (1 - beta1) * g          (every row decays)
+//     v <- v * beta2;  v[idx] += (1 - beta2) * g * g
+//     var <- var - lr_t * m / (sqrt(v) + eps)              (every row moves)
+// with lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) computed by the host wrapper.  So one
+// 64-pair step streams all of E, m, v: 24 * N * ld bytes -- a pure HBM-bandwidth kernel.
+// One warp per row (float4 per lane at ld = 128); the row -> gradient-slot map written by
+// gg_pair_grad tells whether the row has a gradient, and is reset here.
+#include "gg_common.cuh"
+
+namespace gg {
+namespace {
+
+__global__ void __launch_bounds__(256) adam_kernel(long long n_node, int ld, float *__restrict__ emb,
+                                                   float *__restrict__ m_emb, float *__restrict__ v_emb,
+                                                   float *__restrict__ bias, float *__restrict__ m_bias,
+                                                   float *__restrict__ v_bias, const float *__restrict__ grad_rows,
+                                                   const float *__restrict__ grad_bias, int *__restrict__ row_slot,
+                                                   float lr_t, float b1, float b2, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+    for (long long row = warp; row < n_node; row += nwarps) {
+        int slot = -1;
+        if (lane == 0) slot = row_slot[row];
+        slot = __shfl_sync(FULL, slot, 0);
+        const size_t ro = (size_t)row * ld;
+        for (int c = 4 * lane; c < ld; c += 128) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (slot >= 0) g = *reinterpret_cast<const float4 *>(grad_rows + (size_t)slot * ld + c);
+            float4 m = *reinterpret_cast<float4 *>(m_emb + ro + c);
+            float4 v = *reinterpret_cast<float4 *>(v_emb + ro + c);
+            float4 x = *reinterpret_cast<float4 *>(emb + ro + c);
+#define GG_ADAM1(f)                                        \
+    m.f = m.f * b1 + omb1 * g.f;                           \
+    v.f = v.f * b2 + omb2 * (g.f * g.f);                   \
+    x.f = x.f - lr_t * m.f / (sqrtf(v.f) + eps);
+            GG_ADAM1(x) GG_ADAM1(y) GG_ADAM1(z) GG_ADAM1(w)
+#undef GG_ADAM1
+            *reinterpret_cast<float4 *>(m_emb + ro + c) = m;
+            *reinterpret_cast<float4 *>(v_emb + ro + c) = v;
+            *reinterpret_cast<float4 *>(emb + ro + c) = x;
+        }
+        if (lane == 0) {
+            const float g = slot >= 0 ? grad_bias[slot] : 0.0f;
+            const float m = m_bias[row] * b1 + omb1 * g;
+            const float v = v_bias[row] * b2 + omb2 * (g * g);
+            m_bias[row] = m; v_bias[row] = v;
+            bias[row] = bias[row] - lr_t * m / (sqrtf(v) + eps);
+            if (slot >= 0) row_slot[row] = -1;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace gg
+
+extern "C" int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias,
+                             float *m_bias, float *v_bias, const int32_t *n_unique, const int32_t *uniq_ids,
+                             const float *grad_rows, const float *grad_bias, int32_t *row_slot, float lr_t, float beta1,
+                             float beta2, float eps, void *stream) {
+    (void)n_unique; (void)uniq_ids;
+    GG_REQUIRE(emb && m_emb && v_emb && bias && m_bias && v_bias && grad_rows && grad_bias && row_slot, "null pointer");
+    GG_REQUIRE(ld > 0 && ld % 32 == 0, "ld must be a positive multiple of 32");
+    if (n_node == 0) return 0;
+    long long blocks = (n_node + 7) / 8;
+    const long long cap = (long long)gg::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    gg::adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n_node, ld, emb, m_emb, v_emb, bias, m_bias,
+                                                                        v_bias, grad_rows, grad_bias, row_slot, lr_t,
+                                                                        beta1, beta2, eps);
+    return gg::check_cuda(cudaGetLastError(), "adam kernel launch");
+}

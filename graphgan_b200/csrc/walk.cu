@@ -1,0 +1,423 @@
+// walk.cu -- K1, the graph-softmax walk sampler (sm_100a).
+//
+// Replaces GraphGAN.sample (reference src/GraphGAN/graph_gan.py:225-270) for a whole batch of
+// roots: one warp owns one walk at a time (persistent CTAs pull walk ids from a global
+// counter).  Per step the warp
+//   1. enumerates the candidate list [father] + children(cur) from the walk CSR and the
+//      root's BFS parent array (children = adjacency entries whose father is cur, in
+//      adjacency order == the reference's list order, graph_gan.py:96,102-105);
+//   2. scores the candidates on demand: generator.all_score[cur, cand] = e_cur . e_cand + b_cand
+//      (generator.py:21) -- four 8-lane groups, each streaming one embedding row per
+//      LDG.128 quartet (one full 128 B line per group per instruction);
+//   3. softmax (utils.py:131-133) + float64 CDF + inverse-CDF draw (numpy legacy
+//      RandomState.choice, called at graph_gan.py:262) with warp shuffles.
+// The arithmetic is the canonical sequence of DESIGN.md section 3 == oracle/gg_oracle.c.
+#include "gg_common.cuh"
+
+namespace gg {
+namespace {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr int SMEM_CAP = 320;  // candidates per warp kept in shared memory (ids + scores)
+
+struct WalkCtx {
+    gg_walk_desc d;
+};
+
+struct Rng {
+    int mode;
+    uint32_t k0, k1, tag;
+    const double *stream;
+    long long n_stream;
+    long long cursor;  // GG_RNG_STREAM only
+    int exhausted;
+    __device__ __forceinline__ double draw(uint32_t root, uint32_t walk, uint32_t step) {
+        if (mode == GG_RNG_PHILOX) {
+            uint32_t a, b;
+            philox4x32_10(root, walk, step, tag, k0, k1, a, b);
+            return u53(a, b);
+        }
+        if (cursor >= n_stream) { exhausted = 1; return 0.0; }
+        return stream[cursor++];
+    }
+};
+
+// softmax + CDF + draw over sc[0..n) (canonical; == ggo_choose).  All lanes return idx.
+__device__ __forceinline__ int choose_index(float *sc, int n, double u, int lane) {
+    float m = -INFINITY;
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, sc[i]);
+    m = warp_max(m);
+    float S = 0.0f;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int i = t0 + lane;
+        float e = 0.0f;
+        if (i < n) { e = exp_c(__fsub_rn(sc[i], m)); sc[i] = e; }
+        const float T = warp_sum_butterfly(e);
+        S = (t0 == 0) ? T : __fadd_rn(S, T);
+    }
+    __syncwarp();
+    double total = 0.0;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int i = t0 + lane;
+        double x = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;
+        x = warp_scan_ks(x, lane);
+        total = __dadd_rn(total, __shfl_sync(FULL, x, 31));
+    }
+    double carry = 0.0;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int i = t0 + lane;
+        double x = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;
+        x = warp_scan_ks(x, lane);
+        const double q = __ddiv_rn(__dadd_rn(carry, x), total);
+        const unsigned hit = __ballot_sync(FULL, (i < n) && (q > u));
+        if (hit) return t0 + __ffs(hit) - 1;
+        carry = __dadd_rn(carry, __shfl_sync(FULL, x, 31));
+    }
+    return n - 1;
+}
+
+// One complete walk, executed by a full warp.  Returns the status.
+template <int CPL>
+__device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slot, uint32_t k, long long w,
+                                        int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
+                                        unsigned long long &raw_steps, unsigned long long &raw_suml,
+                                        unsigned long long &overflow) {
+    const int grp = lane >> 3, g = lane & 7;
+    const int root = d.roots[slot];
+    const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
+    const int ld = d.ld;
+    int cur = root, prev = -1, step = 0, fedge = -1, plen = 0;
+    int steps = 0, suml = 0, status = GG_NOTRUN, sample = -1;
+    int32_t *prow = (d.max_path > 0 && d.paths) ? d.paths + (size_t)w * (size_t)d.max_path : nullptr;
+    if (prow && lane == 0) prow[0] = cur;
+    plen = 1;
+
+    for (;;) {
+        // ---- candidate list (graph_gan.py:250-259)
+        bool inc_father = step > 0;
+        if (d.for_d && step == 1) inc_father = false;
+        if (!d.for_d && step == 1 && ((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u)) inc_father = false;
+        const long long a0 = d.indptr[cur], a1 = d.indptr[cur + 1];
+        const bool in_smem = (a1 - a0 + 1) <= SMEM_CAP;
+        int *ids = in_smem ? s_ids : g_ids;
+        float *sc = in_smem ? s_sc : g_sc;
+        int n = 0;
+        if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
+        for (long long e0 = a0; e0 < a1; e0 += 32) {
+            const long long e = e0 + lane;
+            int v = -1;
+            if (e < a1) v = __ldg(d.adj + e);
+            const bool isc = (v >= 0) && (__ldg(par + v) == cur);
+            const unsigned mk = __ballot_sync(FULL, isc);
+            if (isc) ids[n + __popc(mk & ((1u << lane) - 1u))] = v;
+            n += __popc(mk);
+        }
+        __syncwarp();
+        if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
+
+        // ---- scores: all_score[cur, cand] (generator.py:21), canonical dot
+        float4 c4[CPL];
+        {
+            const float *crow = d.emb + (size_t)cur * (size_t)ld + 4 * g;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) c4[c] = ldg4(crow + 32 * c);
+        }
+        for (int i0 = 0; i0 < n; i0 += 8) {
+            const int ia = i0 + grp, ib = i0 + 4 + grp;
+            const bool va = ia < n, vb = ib < n;
+            const int ca = va ? ids[ia] : cur, cb = vb ? ids[ib] : cur;
+            const float *ra = d.emb + (size_t)ca * (size_t)ld + 4 * g;
+            const float *rb = d.emb + (size_t)cb * (size_t)ld + 4 * g;
+            float4 xa[CPL], xb[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) xa[c] = ldg4(ra + 32 * c);
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) xb[c] = ldg4(rb + 32 * c);
+            const float ba = __ldg(d.bias + ca), bb = __ldg(d.bias + cb);
+            float sa = 0.0f, sb = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) sa = fma4(c4[c], xa[c], sa);
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) sb = fma4(c4[c], xb[c], sb);
+            sa = group8_sum(sa);
+            sb = group8_sum(sb);
+            if (g == 0) {
+                if (va) sc[ia] = __fadd_rn(sa, ba);
+                if (vb) sc[ib] = __fadd_rn(sb, bb);
+            }
+        }
+        __syncwarp();
+
+        // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
+        const double u = rng.draw((uint32_t)root, k, (uint32_t)step);
+        if (rng.exhausted) { status = GG_NOTRUN; break; }
+        const int idx = choose_index(sc, n, u, lane);
+        const int nxt = ids[idx];
+        __syncwarp();
+        if (step == 0) fedge = (int)(a0 + idx);  // every walk-CSR neighbour of the root is its child
+        if (prow && lane == 0 && plen < d.max_path) prow[plen] = nxt;
+        ++plen;
+        ++steps; suml += n;
+        if (inc_father && idx == 0) { sample = cur; status = GG_DONE; break; }  // graph_gan.py:264-266
+        prev = cur; cur = nxt; ++step;
+    }
+    raw_steps += (unsigned)steps; raw_suml += (unsigned)suml;
+    if (lane == 0) {
+        d.samples[w] = sample;
+        d.status[w] = status;
+        d.first_edge[w] = fedge;
+        d.wsteps[w] = steps;
+        d.wsuml[w] = suml;
+        if (d.path_len) d.path_len[w] = (status == GG_DONE) ? plen : 0;
+    }
+    if (status == GG_DONE && d.max_path > 0 && plen > d.max_path) overflow += 1;
+    return status;
+}
+
+// ---------------------------------------------------------------- order-free (Philox) kernel
+template <int CPL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_kernel(const __grid_constant__ gg_walk_desc d) {
+    __shared__ int s_ids[WARPS_PER_CTA][SMEM_CAP];
+    __shared__ float s_sc[WARPS_PER_CTA][SMEM_CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
+    int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
+    float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
+    Rng rng;
+    rng.mode = GG_RNG_PHILOX; rng.k0 = (uint32_t)d.seed; rng.k1 = (uint32_t)(d.seed >> 32); rng.tag = d.pass_tag;
+    rng.stream = nullptr; rng.n_stream = 0; rng.cursor = 0; rng.exhausted = 0;
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0;
+    const bool ratio_all = d.update_ratio >= 1.0;
+
+    for (;;) {
+        unsigned int wi = 0;
+        if (lane == 0) wi = atomicAdd(d.work_counter, 1u);
+        wi = __shfl_sync(FULL, wi, 0);
+        const long long w = wi;
+        if (w >= d.n_walks) break;
+        // walk -> root slot: last slot with walk_ptr[slot] <= w
+        long long lo = 0, hi = d.n_roots;
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (__ldg(d.walk_ptr + mid) <= w) lo = mid; else hi = mid;
+        }
+        const int slot = (int)lo;
+        const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
+        if (!ratio_all) {  // graph_gan.py:189/209: one draw per root
+            uint32_t a, b;
+            philox4x32_10((uint32_t)d.roots[slot], 0xffffffffu, 0u, rng.tag, rng.k0, rng.k1, a, b);
+            if (!(u53(a, b) < d.update_ratio)) {
+                if (lane == 0) {
+                    d.samples[w] = -1; d.status[w] = GG_SKIPPED; d.first_edge[w] = -1; d.wsteps[w] = 0; d.wsuml[w] = 0;
+                    if (d.path_len) d.path_len[w] = 0;
+                }
+                continue;
+            }
+        }
+        walk_one<CPL>(d, rng, slot, k, w, s_ids[wid], s_sc[wid], g_ids, g_sc, lane, raw_steps, raw_suml, overflow);
+    }
+    if (lane == 0) {
+        if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
+        if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
+        if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
+    }
+}
+
+// ---------------------------------------------------------------- reference-order (stream) kernel
+// One warp replays the reference's sequential consumption of a uniform stream: a draw per
+// root (graph_gan.py:189/209), a draw per choice (:262), stop at a root's first void.
+template <int CPL>
+__global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__ gg_walk_desc d) {
+    __shared__ int s_ids[SMEM_CAP];
+    __shared__ float s_sc[SMEM_CAP];
+    const int lane = threadIdx.x;
+    int *g_ids = reinterpret_cast<int *>(d.scratch);
+    float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
+    Rng rng;
+    rng.mode = GG_RNG_STREAM; rng.k0 = rng.k1 = rng.tag = 0;
+    rng.stream = d.stream; rng.n_stream = d.n_stream; rng.cursor = 0; rng.exhausted = 0;
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0;
+    for (long long slot = 0; slot < d.n_roots && !rng.exhausted; ++slot) {
+        const long long w0 = d.walk_ptr[slot], w1 = d.walk_ptr[slot + 1];
+        const double ur = rng.draw(0, 0, 0);
+        const bool skip = !(ur < d.update_ratio);
+        bool dead = skip || rng.exhausted;
+        for (long long w = w0; w < w1; ++w) {
+            if (dead) {
+                if (lane == 0) {
+                    d.samples[w] = -1; d.status[w] = skip ? GG_SKIPPED : GG_NOTRUN; d.first_edge[w] = -1;
+                    d.wsteps[w] = 0; d.wsuml[w] = 0;
+                    if (d.path_len) d.path_len[w] = 0;
+                }
+                continue;
+            }
+            const int st = walk_one<CPL>(d, rng, (int)slot, (uint32_t)(w - w0), w, s_ids, s_sc, g_ids, g_sc, lane,
+                                         raw_steps, raw_suml, overflow);
+            if (st != GG_DONE) dead = true;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
+        atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
+        atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
+        d.counters[GG_CNT_STREAM_USED] = (unsigned long long)rng.cursor + (rng.exhausted ? (1ull << 62) : 0ull);
+    }
+}
+
+// ---------------------------------------------------------------- finalize (one warp per root)
+__global__ void finalize_kernel(long long n_roots, const long long *walk_ptr, int for_d, int *samples, int *status,
+                                const int *first_edge, int *wsteps, int *wsuml, int *path_len, uint32_t *d1_bits,
+                                int *root_ok, unsigned long long *counters) {
+    const int lane = threadIdx.x & 31;
+    const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= n_roots) return;
+    const long long w0 = walk_ptr[slot], w1 = walk_ptr[slot + 1];
+    // first walk that is not DONE (void, skipped or never run)
+    long long first_bad = w1;
+    for (long long w = w0 + lane; w < w1; w += 32)
+        if (status[w] != GG_DONE) { first_bad = w; break; }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const long long o = __shfl_xor_sync(FULL, first_bad, off);
+        first_bad = o < first_bad ? o : first_bad;
+    }
+    const bool ok = (first_bad == w1) && (w1 > w0);
+    unsigned long long steps = 0, suml = 0;
+    for (long long w = w0 + lane; w < w1; w += 32) {
+        if (w <= first_bad) {
+            steps += (unsigned)wsteps[w]; suml += (unsigned)wsuml[w];
+            if (for_d && status[w] == GG_DONE) {
+                const int e = first_edge[w];
+                if (e >= 0) atomicOr(d1_bits + (e >> 5), 1u << (e & 31));
+            }
+        } else {  // the reference never ran these (graph_gan.py:252-257 returned early)
+            if (status[w] != GG_SKIPPED) status[w] = GG_NOTRUN;
+            samples[w] = -1; wsteps[w] = 0; wsuml[w] = 0;
+            if (path_len) path_len[w] = 0;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        steps += __shfl_xor_sync(FULL, steps, off);
+        suml += __shfl_xor_sync(FULL, suml, off);
+    }
+    if (lane == 0) {
+        root_ok[slot] = ok ? 1 : 0;
+        if (steps) atomicAdd(counters + GG_CNT_STEPS, steps);
+        if (suml) atomicAdd(counters + GG_CNT_SUML, suml);
+        if (ok) {
+            atomicAdd(counters + GG_CNT_ACCEPTED, (unsigned long long)(w1 - w0));
+            atomicAdd(counters + GG_CNT_OK_ROOTS, 1ull);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- D rows
+__global__ void row_count_kernel(long long n_roots, const long long *walk_ptr, const int *root_ok, long long *row_ptr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_roots) row_ptr[i] = root_ok[i] ? 2 * (walk_ptr[i + 1] - walk_ptr[i]) : 0;
+}
+
+__global__ void emit_rows_kernel(long long n_roots, const int *roots, const long long *walk_ptr,
+                                 const long long *pos_indptr, const int *pos_flat, const int *root_ok,
+                                 const int *samples, const long long *row_ptr, int *center, int *neighbor, int *label) {
+    const int lane = threadIdx.x & 31;
+    const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= n_roots || !root_ok[slot]) return;
+    const int r = roots[slot];
+    const long long k = walk_ptr[slot + 1] - walk_ptr[slot];
+    const long long o = row_ptr[slot], p0 = pos_indptr[r], w0 = walk_ptr[slot];
+    for (long long t = lane; t < k; t += 32) {  // graph_gan.py:194-201
+        center[o + t] = r; neighbor[o + t] = pos_flat[p0 + t]; label[o + t] = 1;
+        center[o + k + t] = r; neighbor[o + k + t] = samples[w0 + t]; label[o + k + t] = 0;
+    }
+}
+
+int grid_ctas() { return sm_count() * 4; }
+
+}  // namespace
+}  // namespace gg
+
+extern "C" int gg_walk_scratch_bytes(int32_t max_cand, int64_t *bytes) {
+    GG_REQUIRE(bytes && max_cand > 0, "bad arguments");
+    const int64_t warps = (int64_t)gg::grid_ctas() * gg::WARPS_PER_CTA;
+    *bytes = warps * 2 * (int64_t)max_cand * 4;
+    return 0;
+}
+
+extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
+    GG_REQUIRE(dp, "null descriptor");
+    const gg_walk_desc &d = *dp;
+    GG_REQUIRE(d.ld > 0 && d.ld % 32 == 0, "ld must be a positive multiple of 32");
+    GG_REQUIRE(d.emb && d.bias && d.indptr && d.adj && d.roots && d.parent && d.walk_ptr, "null graph/embedding pointer");
+    GG_REQUIRE(d.samples && d.status && d.first_edge && d.wsteps && d.wsuml && d.counters && d.work_counter,
+               "null output pointer");
+    GG_REQUIRE(d.for_d || d.d1_bits, "G mode needs d1_bits");
+    GG_REQUIRE(d.n_walks < (1ll << 32), "too many walks in one call");
+    GG_REQUIRE(d.max_cand > 0 && d.scratch, "scratch missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));
+    if (d.n_walks == 0 || d.n_roots == 0) return 0;
+    const int cpl = d.ld / 32;
+    if (d.rng_mode == GG_RNG_STREAM) {
+        GG_REQUIRE(d.stream, "stream mode needs the uniform stream");
+        GG_REQUIRE(d.scratch_bytes >= 2ll * d.max_cand * 4, "scratch too small");
+        switch (cpl) {
+            case 1: gg::walk_stream_kernel<1><<<1, 32, 0, st>>>(d); break;
+            case 2: gg::walk_stream_kernel<2><<<1, 32, 0, st>>>(d); break;
+            case 4: gg::walk_stream_kernel<4><<<1, 32, 0, st>>>(d); break;
+            case 8: gg::walk_stream_kernel<8><<<1, 32, 0, st>>>(d); break;
+            default: gg::set_error("gg_walk_sample: unsupported ld %d (supported: 32, 64, 128, 256)", d.ld); return 2;
+        }
+    } else {
+        const int ctas = gg::grid_ctas();
+        GG_REQUIRE(d.scratch_bytes >= (int64_t)ctas * gg::WARPS_PER_CTA * 2 * d.max_cand * 4, "scratch too small");
+        switch (cpl) {
+            case 1: gg::walk_kernel<1><<<ctas, gg::WARPS_PER_CTA * 32, 0, st>>>(d); break;
+            case 2: gg::walk_kernel<2><<<ctas, gg::WARPS_PER_CTA * 32, 0, st>>>(d); break;
+            case 4: gg::walk_kernel<4><<<ctas, gg::WARPS_PER_CTA * 32, 0, st>>>(d); break;
+            case 8: gg::walk_kernel<8><<<ctas, gg::WARPS_PER_CTA * 32, 0, st>>>(d); break;
+            default: gg::set_error("gg_walk_sample: unsupported ld %d (supported: 32, 64, 128, 256)", d.ld); return 2;
+        }
+    }
+    return gg::check_cuda(cudaGetLastError(), "walk kernel launch");
+}
+
+extern "C" int gg_walk_finalize(int64_t n_roots, const int64_t *walk_ptr, int32_t for_d, int32_t *samples,
+                                int32_t *status, const int32_t *first_edge, int32_t *wsteps, int32_t *wsuml,
+                                int32_t *path_len, uint32_t *d1_bits, int32_t *root_ok,
+                                unsigned long long *counters, void *stream) {
+    GG_REQUIRE(walk_ptr && samples && status && first_edge && wsteps && wsuml && root_ok && counters, "null pointer");
+    GG_REQUIRE(!for_d || d1_bits, "D mode needs d1_bits");
+    if (n_roots == 0) return 0;
+    const int threads = 256;
+    const long long blocks = (n_roots * 32 + threads - 1) / threads;
+    gg::finalize_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        n_roots, (const long long *)walk_ptr, for_d, samples, status, first_edge, wsteps, wsuml, path_len, d1_bits,
+        root_ok, counters);
+    return gg::check_cuda(cudaGetLastError(), "finalize kernel launch");
+}
+
+extern "C" int gg_emit_d_rows(int64_t n_roots, const int32_t *roots, const int64_t *walk_ptr,
+                              const int64_t *pos_indptr, const int32_t *pos_flat, const int32_t *root_ok,
+                              const int32_t *samples, int64_t *row_ptr, int32_t *center, int32_t *neighbor,
+                              int32_t *label, int64_t *n_rows_out, void *stream) {
+    GG_REQUIRE(roots && walk_ptr && pos_indptr && pos_flat && root_ok && samples && row_ptr && n_rows_out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 256;
+    if (n_roots > 0) {
+        gg::row_count_kernel<<<(unsigned)((n_roots + threads - 1) / threads), threads, 0, st>>>(
+            n_roots, (const long long *)walk_ptr, root_ok, (long long *)row_ptr);
+        GG_CHECK(cudaGetLastError());
+    }
+    int rc = gg::launch_exclusive_scan_i64((long long *)row_ptr, n_roots, (long long *)n_rows_out, st);
+    if (rc) return rc;
+    if (n_roots == 0) return 0;
+    GG_REQUIRE(center && neighbor && label, "null output pointer");
+    const long long blocks = (n_roots * 32 + threads - 1) / threads;
+    gg::emit_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(n_roots, roots, (const long long *)walk_ptr,
+                                                               (const long long *)pos_indptr, pos_flat, root_ok,
+                                                               samples, (const long long *)row_ptr, center, neighbor,
+                                                               label);
+    return gg::check_cuda(cudaGetLastError(), "emit rows launch");
+}

@@ -1,0 +1,165 @@
+/*
+ * graphgan_b200.h -- C ABI of libgraphgan_b200.so, the B200 (sm_100a) implementation of
+ * GraphGAN's scoring-and-sampling hot path.
+ *
+ * The reference (hwwang55/GraphGAN) has no native code and no FFI: its seam is the five
+ * tf.Session.run(fetch, feed_dict) call sites of src/GraphGAN/graph_gan.py (154, 173, 220,
+ * 238, 298).  Each entry point below states the reference code it replaces; the Python
+ * binding a maintainer adds is shown in INTEGRATION.md (ctypes, graphgan_b200/_cabi.py).
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller (in the
+ *     Python host: torch tensors used only as memory containers, passed as data_ptr()).
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it, no hidden
+ *     synchronisation, no allocation.  Scratch is caller supplied (query *_scratch_bytes).
+ *   - return 0 on success, non-zero on CUDA / argument error; gg_last_error() gives the
+ *     message for the calling thread.  Nothing aborts.
+ *   - embedding rows are fp32 [N, ld] with ld = round_up(n_emb, 32), zero padded.
+ *   - graph = two CSRs in the reference's adjacency-file order (src/utils.py:27-37):
+ *       raw  : graph[i] as read (duplicates and self-loops kept) -> positives, sample_num
+ *       walk : first occurrences only, self-loops dropped        -> BFS trees and walks
+ */
+#ifndef GRAPHGAN_B200_H
+#define GRAPHGAN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GG_ABI_VERSION 1
+
+/* walk status codes (per walk) */
+enum { GG_NOTRUN = 0, GG_DONE = 1, GG_VOID = 2, GG_SKIPPED = 3 };
+/* rng modes */
+enum {
+    GG_RNG_PHILOX = 0, /* Philox4x32-10, key=(seed), counter=(root, walk, step, pass_tag): order free */
+    GG_RNG_STREAM = 1  /* caller supplied doubles consumed in the reference's sequential order
+                          (np.random.rand at graph_gan.py:189/209, np.random.choice at :262) */
+};
+/* counters[] slots written by gg_walk_finalize (reference semantics: walks after a root's
+ * first voiding walk do not exist) */
+enum {
+    GG_CNT_STEPS = 0, GG_CNT_SUML = 1, GG_CNT_ACCEPTED = 2, GG_CNT_OK_ROOTS = 3,
+    GG_CNT_PATH_OVERFLOW = 4, GG_CNT_RAW_STEPS = 5, GG_CNT_RAW_SUML = 6, GG_CNT_STREAM_USED = 7,
+    GG_CNT_SLOTS = 8
+};
+
+const char *gg_last_error(void);
+int gg_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1: graph-softmax walk.  Replaces GraphGAN.sample (graph_gan.py:225-270) together with the
+ * generator.all_score fetch at :238 (scores are computed on demand for the candidates only,
+ * generator.py:21), utils.softmax (utils.py:131-133) and np.random.choice's inverse-CDF
+ * draw (:262), for a whole batch of roots at once.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gg_walk_desc {
+    int64_t n_node;
+    int32_t ld;                 /* row stride in floats, multiple of 32 */
+    const float *emb;           /* device [N, ld]  generator.embedding_matrix (generator.py:11-14) */
+    const float *bias;          /* device [N]      generator.bias_vector      (generator.py:15)    */
+    const int64_t *indptr;      /* device [N+1]    walk CSR */
+    const int32_t *adj;         /* device [nnz]    */
+    int64_t n_roots;
+    const int32_t *roots;       /* device [R] root node ids (batch order = reference root order) */
+    const int32_t *parent;      /* device [R, N] BFS fathers (gg_bfs_build); root & unreachable = -1 */
+    const int64_t *walk_ptr;    /* device [R+1] exclusive prefix of per-root sample_num */
+    int64_t n_walks;            /* = walk_ptr[R] */
+    int32_t for_d;              /* graph_gan.py:225 `for_d` */
+    int32_t rng_mode;
+    uint32_t *d1_bits;          /* device bitset over walk-CSR entries: "father entry removed"
+                                   (the in-place tree mutation of graph_gan.py:258-259).
+                                   G mode reads it here; D mode sets it in gg_walk_finalize */
+    uint64_t seed;
+    uint32_t pass_tag;
+    int32_t max_path;           /* row stride of paths (0: paths not recorded) */
+    const double *stream;       /* device, GG_RNG_STREAM only */
+    int64_t n_stream;
+    double update_ratio;        /* config.update_ratio (graph_gan.py:189/209) */
+    int32_t max_cand;           /* >= max walk-CSR degree + 1 */
+    int32_t reserved;
+    /* per-walk outputs, device [W] */
+    int32_t *samples;           /* sampled node (graph_gan.py:265) or -1 */
+    int32_t *status;
+    int32_t *first_edge;        /* walk-CSR entry of the depth-1 node chosen at the root step */
+    int32_t *wsteps;            /* choices made */
+    int32_t *wsuml;             /* sum of candidate-list lengths */
+    int32_t *paths;             /* device [W, max_path] or NULL */
+    int32_t *path_len;          /* device [W] or NULL */
+    unsigned long long *counters; /* device [GG_CNT_SLOTS] */
+    void *scratch;              /* device, gg_walk_scratch_bytes(max_cand) */
+    int64_t scratch_bytes;
+    unsigned int *work_counter; /* device, 1 word, zeroed by the call */
+} gg_walk_desc;
+
+int gg_walk_scratch_bytes(int32_t max_cand, int64_t *bytes);
+int gg_walk_sample(const gg_walk_desc *d, void *stream);
+
+/* Per root: find the first voiding walk (graph_gan.py:252-257 returns None for the WHOLE
+ * root), blank the walks after it, set root_ok ("neg is not None and len(pos) != 0",
+ * graph_gan.py:192), apply the father-removal bits of the surviving D walks, and reduce the
+ * counters. */
+int gg_walk_finalize(int64_t n_roots, const int64_t *walk_ptr, int32_t for_d, int32_t *samples,
+                     int32_t *status, const int32_t *first_edge, int32_t *wsteps, int32_t *wsuml,
+                     int32_t *path_len, uint32_t *d1_bits, int32_t *root_ok,
+                     unsigned long long *counters, void *stream);
+
+/* prepare_data_for_d's output rows (graph_gan.py:192-201): for every accepted root, in batch
+ * order: [i]*k + [i]*k | pos + neg | 1*k + 0*k.  row_ptr: device [R+1] scratch/out (exclusive
+ * scan of 2*len(pos) over accepted roots); n_rows_out: device int64. */
+int gg_emit_d_rows(int64_t n_roots, const int32_t *roots, const int64_t *walk_ptr,
+                   const int64_t *pos_indptr, const int32_t *pos_flat, const int32_t *root_ok,
+                   const int32_t *samples, int64_t *row_ptr, int32_t *center, int32_t *neighbor,
+                   int32_t *label, int64_t *n_rows_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tree construction: GraphGAN.construct_trees (graph_gan.py:84-108) for a batch of roots, as
+ * parent arrays (first discoverer in FIFO / adjacency order).  parent: device [R, N].
+ * ------------------------------------------------------------------------------------------ */
+int gg_bfs_scratch_bytes(int64_t n_node, int64_t *bytes);
+int gg_bfs_build(int64_t n_node, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
+                 const int32_t *roots, int32_t *parent, void *scratch, int64_t scratch_bytes,
+                 void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2: pair scoring.  score_k = e_{i_k}.e_{j_k} + b_{j_k} (discriminator.py:21-24 /
+ * generator.py:22-25).
+ * ------------------------------------------------------------------------------------------ */
+/* discriminator.reward (discriminator.py:33-34): log(1 + exp(clip(score, -10, 10))) */
+int gg_pair_reward(int64_t n_pairs, const int32_t *node_id, const int32_t *node_neighbor_id,
+                   const float *emb, const float *bias, int32_t ld, float *reward, void *stream);
+/* generator.all_score rows (generator.py:21) for small N only (tests / source compat) */
+int gg_all_score(int64_t n_node, const float *emb, const float *bias, int32_t ld, float *out,
+                 void *stream);
+
+/* Sparse gradient of one mini-batch (<= GG_MAX_BATCH pairs), duplicates summed in pair order
+ * (TF1.8 AdamOptimizer._apply_sparse_duplicate_indices: unique + segment_sum):
+ *   mode 0 = discriminator loss (discriminator.py:26-30), aux = label
+ *   mode 1 = generator loss     (generator.py:26-29),     aux = reward
+ * outputs: n_unique (device int32), uniq_ids[2B], grad_rows[2B, ld], grad_bias[2B],
+ * row_slot: device [N] int32 map, must be all -1 on entry; set for touched rows. */
+#define GG_MAX_BATCH 1024
+int gg_pair_grad(int32_t mode, int32_t n_pairs, const int32_t *node_id,
+                 const int32_t *node_neighbor_id, const float *aux, const float *emb,
+                 const float *bias, int32_t ld, float lambda, int32_t *n_unique, int32_t *uniq_ids,
+                 float *grad_rows, float *grad_bias, int32_t *row_slot, void *stream);
+
+/* K3: TF1.8 AdamOptimizer sparse apply == dense decay (generator.py:30-31,
+ * discriminator.py:31-32): m <- b1*m (+ (1-b1) g on touched rows), v likewise, then for ALL
+ * rows var -= lr_t * m / (sqrt(v) + eps).  Resets row_slot to -1. */
+int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias,
+                  float *m_bias, float *v_bias, const int32_t *n_unique, const int32_t *uniq_ids,
+                  const float *grad_rows, const float *grad_bias, int32_t *row_slot, float lr_t,
+                  float beta1, float beta2, float eps, void *stream);
+
+/* get_node_pairs_from_path (graph_gan.py:272-291) for a batch of recorded paths.
+ * pair_ptr: device [W+1] (out, exclusive scan of per-path pair counts). */
+int gg_window_pairs(int64_t n_walks, const int32_t *paths, const int32_t *path_len, int32_t max_path,
+                    int32_t window, int64_t *pair_ptr, int32_t *node_1, int32_t *node_2,
+                    int64_t *n_pairs_out, int64_t capacity, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,161 @@
+"""GPU parity of K1 (walk sampler) and the BFS-tree builder against the oracles.
+
+Everything goes through the C ABI (graphgan_b200._cabi -> libgraphgan_b200.so).  Bars:
+bit-exact node indices, statuses, root_ok flags, tree-mutation bits, D rows and paths.
+"""
+import numpy as np
+import pytest
+
+from tests.golden import loader
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(case, cuda_device, roots=None):
+    import torch
+    from graphgan_b200 import graph as G, sampler as S
+    from oracle import canonical as can
+    edges = case["train_edges"]
+    hg = G.HostGraph(edges, case["test_edges"])
+    assert hg.n_node == case.n
+    # host graph == the reference reader's graph (utils.py:12-47)
+    ptr, flat = can.raw_csr(case.graph)
+    assert np.array_equal(hg.raw_indptr, ptr) and np.array_equal(hg.raw_adj, flat)
+    indptr, adj = can.unique_csr(case.graph)
+    assert np.array_equal(hg.indptr, indptr) and np.array_equal(hg.adj, adj)
+    dg = G.DeviceGraph(hg, cuda_device)
+    smp = S.WalkSampler(dg)
+    roots = np.arange(case.n, dtype=np.int32) if roots is None else np.asarray(roots, np.int32)
+    trees = smp.build_trees(roots)
+    emb = S.pad_embedding(case.emb_g, cuda_device)
+    bias = torch.as_tensor(case.bias_g).to(cuda_device)
+    return hg, dg, smp, roots, trees, emb, bias
+
+
+def _bits_to_set(bits, indptr, adj):
+    out = set()
+    words = np.asarray(bits).view(np.uint32)
+    for w in np.flatnonzero(words):
+        for b in range(32):
+            if (words[w] >> b) & 1:
+                e = int(w) * 32 + b
+                r = int(np.searchsorted(indptr, e, side="right") - 1)
+                out.add((r, int(adj[e])))
+    return out
+
+
+@pytest.mark.parametrize("name", ["tiny", "rand300", "rand1200", "cagrqc"])
+def test_bfs_matches_reference_order(name, cuda_device):
+    from oracle import canonical as can
+    case = loader.load(name)
+    rs = np.random.RandomState(1)
+    roots = np.arange(case.n) if case.n <= 1200 else np.sort(rs.choice(case.n, 600, replace=False))
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots)
+    got = trees.parent.cpu().numpy()
+    want = can.bfs_parents(hg.indptr, hg.adj, roots)
+    assert np.array_equal(got, want)
+    if "parent" in case:  # the reference's own dict trees (construct_trees) as parent arrays
+        assert np.array_equal(got, case["parent"][roots])
+
+
+@pytest.mark.parametrize("name", ["tiny", "rand300", "rand1200", "cagrqc"])
+def test_stream_replay_matches_reference(name, cuda_device):
+    """Feed the MT19937 doubles the reference consumed; the GPU must reproduce the reference's
+    prepare_data_for_d rows, its tree mutations, and then (G pass on the mutated trees) its paths."""
+    import torch
+    from graphgan_b200 import sampler as S
+    case = loader.load(name)
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device)
+    st = torch.as_tensor(loader.stream(case)).to(cuda_device)
+    out = smp.run(emb, bias, trees, dg.raw_deg, True, rng_mode=S.RNG_STREAM, stream=st)
+    c, nb, lb, n_rows = smp.emit_d_rows(out)
+    n_rows = int(n_rows.item())
+    assert n_rows == case.d_center.shape[0]
+    assert np.array_equal(c[:n_rows].cpu().numpy(), case.d_center)
+    assert np.array_equal(nb[:n_rows].cpu().numpy(), case.d_neighbor)
+    assert np.array_equal(lb[:n_rows].cpu().numpy(), case.d_labels)
+    cnt = out.counters_host()
+    assert cnt["stream_used"] == int(case.d_draws)
+    assert cnt["steps"] == case.dtr_chosen.shape[0]
+    assert _bits_to_set(dg.d1_bits.cpu().numpy(), hg.indptr, hg.adj) == set(map(tuple, case.mutated.tolist()))
+    # G pass continues on the same stream
+    used = cnt["stream_used"]
+    out_g = smp.run(emb, bias, trees, int(case.n_sample_gen), False, rng_mode=S.RNG_STREAM, stream=st[used:], max_path=48)
+    cg = out_g.counters_host()
+    assert cg["path_overflow"] == 0
+    assert used + cg["stream_used"] == int(case.total_draws)
+    status = out_g.status.cpu().numpy()
+    plen = out_g.path_len.cpu().numpy()
+    paths = out_g.paths.cpu().numpy()
+    got = [paths[w, :plen[w]].tolist() for w in np.flatnonzero(status == S.DONE)]
+    assert len(got) == int(case.g_n_paths)
+    pp, pf = case.g_paths_ptr, case.g_paths_flat
+    for k in range(pp.shape[0] - 1):
+        assert got[k] == pf[pp[k]:pp[k + 1]].tolist()
+
+
+def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen):
+    import torch
+    from graphgan_b200 import sampler as S
+    from oracle import canonical as can
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots)
+    par = trees.parent.cpu().numpy()
+    E = can.pad_rows(case.emb_g)
+    bits = np.zeros(dg.n_bit_words, np.uint32)
+    deg = hg.degrees()[roots]
+    ref = can.walk_pass(E, case.bias_g, hg.indptr, hg.adj, roots, par, deg, True, bits, seed=seed, pass_tag=3,
+                        update_ratio=update_ratio)
+    sn = torch.as_tensor(deg.astype(np.int64)).to(cuda_device)
+    out = smp.run(emb, bias, trees, sn, True, seed=seed, pass_tag=3, update_ratio=update_ratio)
+    assert np.array_equal(out.root_ok.cpu().numpy()[:len(roots)], ref.root_ok)
+    assert np.array_equal(out.status.cpu().numpy()[:ref.status.shape[0]], ref.status)
+    assert np.array_equal(out.samples.cpu().numpy()[:ref.samples.shape[0]], ref.samples)
+    assert np.array_equal(out.wsteps.cpu().numpy()[:ref.wsteps.shape[0]], ref.wsteps)
+    assert np.array_equal(out.wsuml.cpu().numpy()[:ref.wsuml.shape[0]], ref.wsuml)
+    assert np.array_equal(dg.d1_bits.cpu().numpy().view(np.uint32), bits)
+    cnt = out.counters_host()
+    assert (cnt["steps"], cnt["sum_l"]) == (ref.steps, ref.sum_l)
+    assert cnt["accepted"] == int(sum(deg[k] for k in range(len(roots)) if ref.root_ok[k]))
+    c, nb, lb, n_rows = smp.emit_d_rows(out)
+    n_rows = int(n_rows.item())
+    rc, rn, rl = can.d_rows(ref, roots, hg.raw_indptr, hg.raw_adj)
+    assert n_rows == rc.shape[0]
+    assert np.array_equal(c[:n_rows].cpu().numpy(), rc) and np.array_equal(nb[:n_rows].cpu().numpy(), rn)
+    assert np.array_equal(lb[:n_rows].cpu().numpy(), rl)
+    # G pass on the mutated trees
+    ref_g = can.walk_pass(E, case.bias_g, hg.indptr, hg.adj, roots, par, np.full(len(roots), n_sample_gen), False, bits,
+                          seed=seed, pass_tag=4, update_ratio=update_ratio, max_path=40)
+    out_g = smp.run(emb, bias, trees, n_sample_gen, False, seed=seed, pass_tag=4, update_ratio=update_ratio, max_path=40)
+    assert np.array_equal(out_g.status.cpu().numpy(), ref_g.status)
+    assert np.array_equal(out_g.samples.cpu().numpy(), ref_g.samples)
+    assert np.array_equal(out_g.path_len.cpu().numpy(), ref_g.path_len)
+    gp, rp = out_g.paths.cpu().numpy(), ref_g.paths
+    for w in np.flatnonzero(ref_g.status == can.DONE):
+        assert np.array_equal(gp[w, :ref_g.path_len[w]], rp[w, :ref_g.path_len[w]])
+    cg = out_g.counters_host()
+    assert (cg["steps"], cg["sum_l"]) == (ref_g.steps, ref_g.sum_l)
+    return cnt, cg
+
+
+@pytest.mark.parametrize("name,ratio", [("tiny", 1.0), ("rand300", 1.0), ("rand300", 0.6), ("rand1200", 1.0), ("cagrqc", 1.0)])
+def test_philox_matches_canonical_oracle(name, ratio, cuda_device):
+    case = loader.load(name)
+    _philox_compare(case, cuda_device, None, ratio, seed=0x1234567 + 17, n_sample_gen=int(case.n_sample_gen))
+
+
+def test_hub_lists_use_global_scratch(cuda_device):
+    """A power-law graph whose hub has > SMEM_CAP neighbours: the long-list (global scratch) path
+    and multi-tile softmax must agree bit-for-bit with the oracle as well."""
+    from graphgan_b200 import synth
+    n, d = 6000, 128
+    edges = synth.power_law(n, 16, seed=3)
+    case = loader.Case(n=n, dim=d, train_edges=edges, test_edges=np.zeros((0, 2), np.int64),
+                       emb_g=synth.embeddings(n, d, seed=5, sigma=0.3), bias_g=np.zeros(n, np.float32))
+    from graphgan_b200 import graph as G
+    hg = G.HostGraph(edges, None, n_node=n)
+    assert hg.max_deg > 400
+    case["graph"] = [hg.neighbors(i).tolist() for i in range(n)]
+    rs = np.random.RandomState(0)
+    roots = np.sort(rs.choice(np.flatnonzero(hg.degrees() > 0), 400, replace=False))
+    cnt, cg = _philox_compare(case, cuda_device, roots, 1.0, seed=99, n_sample_gen=6)
+    assert cnt["steps"] > 0
