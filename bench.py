@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- sampled negative edges / second of the D-sampling pass (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic input: every walk of
+``prepare_data_for_d`` (reference src/GraphGAN/graph_gan.py:182-202 -> sample :225-270) for R
+resident roots -- K1 (walk kernel) + finalize + row emission.  Workload at N=1: BASELINE.json
+configs[2], synthetic power-law N=1M, avg-deg 20, n_emb=128 (the configuration the metric is
+quoted on).  Multi-GPU: every rank holds the replicated graph/embeddings and its own R roots
+(weak scaling, no data-path collective -- SURVEY.md section 8e).
+
+  python bench.py [--gpus N --steps K --warmup W]         # one JSON line on rank 0
+  python bench.py --impl reference ...                    # the reference's CPU path (oracle T0, all host threads)
+
+The CUDA path never touches oracle/; only the cpu_baseline / --impl reference legs do.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (generator, N, avg_deg, d)
+    "powerlaw_1m": ("power_law", 1_000_000, 20, 128),     # BASELINE.json configs[2] / [3]
+    "er_100k": ("erdos_renyi", 100_000, 10, 128),         # configs[1]
+    "powerlaw_100k": ("power_law", 100_000, 10, 128),     # smoke-sized
+}
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="powerlaw_1m", choices=sorted(WORKLOADS))
+    p.add_argument("--roots", type=int, default=4096, help="resident roots per GPU (R)")
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def make_inputs(args, rank):
+    from graphgan_b200 import graph as G, synth
+    gen, n, deg, d = WORKLOADS[args.workload]
+    cache = "/tmp/gg_bench_cache/%s_seed%d.npy" % (args.workload, args.seed)
+    try:
+        edges = np.load(cache)
+    except (OSError, ValueError):
+        edges = getattr(synth, gen)(n, deg, seed=args.seed)
+        try:   # best effort: the reference arm and every rank regenerate the same edge list otherwise
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            tmp = "%s.%d.tmp.npy" % (cache, os.getpid())
+            np.save(tmp, edges)
+            os.replace(tmp, cache)
+        except OSError:
+            pass
+    hg = G.HostGraph(edges, None, n_node=n)
+    emb = synth.embeddings(n, d, seed=args.seed + 1)
+    roots = synth.pick_roots(hg.degrees(), args.roots, seed=args.seed + 101 * rank)
+    return hg, emb, roots, d
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle; checker only)
+_SH = {}   # inherited by forked workers: graph, embeddings, parent arrays of the sample
+
+
+class _AdjView:
+    def __init__(self, indptr, adj):
+        self.indptr, self.adj = indptr, adj
+
+    def __getitem__(self, i):
+        return self.adj[self.indptr[i]:self.indptr[i + 1]]
+
+
+class _GraphView:
+    """graph[i] for the sampled roots only: prepare_data_for_d needs the list and its length."""
+
+    def __init__(self, hg, roots):
+        self.d = {int(r): hg.neighbors(int(r)).tolist() for r in roots}
+
+    def __getitem__(self, i):
+        return self.d[i]
+
+    def __len__(self):
+        return len(self.d)
+
+
+def _bfs_chunk(rng):
+    from oracle import canonical as can
+    lo, hi = rng
+    hg = _SH["hg"]
+    _SH["par"][lo:hi] = can.bfs_parents(hg.indptr, hg.adj, _SH["sample"][lo:hi])
+    return hi - lo
+
+
+def _sample_chunk(job):
+    """The reference's prepare_data_for_d -> sample(for_d=True) (oracle T0, lazy score) over roots[lo:hi]."""
+    from oracle import faithful
+    lo, hi, seed = job
+    hg, emb, roots, par = _SH["hg"], _SH["emb"], _SH["sample"][lo:hi], _SH["par"]
+    trees = faithful.ParentTrees(_AdjView(hg.indptr, hg.adj), {int(r): par[lo + k] for k, r in enumerate(roots)})
+    F = faithful.Faithful(_GraphView(hg, roots), emb, bias_g=_SH["bias"], rng=np.random.RandomState(seed),
+                          score_mode="lazy", trees=trees)
+    t0 = time.time()
+    F.prepare_data_for_d(roots=[int(r) for r in roots])
+    return F.stats["neg_edges"], F.stats["steps"], F.stats["sum_l"], time.time() - t0
+
+
+class CpuReference:
+    """Bounded sample of the workload's roots, trees built once (the reference caches them too),
+    then timed passes of the reference sampling logic on `workers` host processes."""
+
+    def __init__(self, hg, emb, roots, seconds, workers, parent_rows=None):
+        import multiprocessing as mp
+        self.mp, self.workers = mp.get_context("fork"), workers
+        _SH.update(hg=hg, emb=emb, bias=np.zeros(hg.n_node, np.float32))
+        # calibrate on 2 roots (evenly spaced: roots are sorted by id and low ids are the hubs)
+        cal = roots[[len(roots) // 3, (2 * len(roots)) // 3]]
+        _SH["sample"] = cal
+        if parent_rows is not None:
+            _SH["par"] = parent_rows(cal)
+        else:
+            _SH["par"] = np.empty((2, hg.n_node), np.int32); _bfs_chunk((0, 2))
+        e, st, sl, dt = _sample_chunk((0, 2, 12345))
+        per_root = max(dt / 2, 1e-4)
+        n = int(min(len(roots), max(2 * workers, workers * seconds / per_root)))
+        n = min(n, 96 * workers)                      # bound the tree memory / BFS time of the sample
+        self.sample = roots[np.unique(np.linspace(0, len(roots) - 1, n).astype(np.int64))]
+        n = len(self.sample)
+        _SH["sample"] = self.sample
+        path = "/dev/shm/gg_bench_par_%d.npy" % os.getpid()
+        self.path = path
+        par = np.lib.format.open_memmap(path, mode="w+", dtype=np.int32, shape=(n, hg.n_node))
+        _SH["par"] = par
+        self.chunks = [(int(c[0]), int(c[-1]) + 1) for c in np.array_split(np.arange(n), workers) if len(c)]
+        if parent_rows is not None:
+            par[:] = parent_rows(self.sample)
+        elif workers == 1:
+            _bfs_chunk((0, n))
+        else:
+            with self.mp.Pool(len(self.chunks)) as pool:
+                pool.map(_bfs_chunk, self.chunks)
+            par.flush()
+
+    def run(self, seed):
+        jobs = [(lo, hi, seed * 1000 + i) for i, (lo, hi) in enumerate(self.chunks)]
+        t0 = time.time()
+        if len(jobs) == 1:
+            res = [_sample_chunk(jobs[0])]
+        else:
+            with self.mp.Pool(len(jobs)) as pool:
+                res = pool.map(_sample_chunk, jobs)
+        dt = time.time() - t0
+        edges = sum(r[0] for r in res)
+        return {"value": edges / dt, "unit": "neg_edges/s", "cores": len(jobs), "kind": "port",
+                "sample": "%d of the workload's roots (%d neg edges, %d walk steps, %d candidates) in %.1f s; "
+                          "oracle T0 lazy-score: the reference's sample()/prepare_data_for_d logic "
+                          "(graph_gan.py:182-270) with numpy standing in for TF1.8, trees prebuilt" % (
+                              len(self.sample), edges, sum(r[1] for r in res), sum(r[2] for r in res), dt)}, dt
+
+    def close(self):
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    hg, emb, roots, d = make_inputs(args, 0)
+    workers = os.cpu_count() or 1
+    per_step_seconds = max(2.0, min(args.cpu_seconds, 150.0 / max(args.steps + args.warmup, 1)))
+    ref = CpuReference(hg, emb, roots, per_step_seconds, workers)
+    times, vals, last = [], [], None
+    for s in range(args.warmup + args.steps):
+        res, dt = ref.run(args.seed + s)
+        if s >= args.warmup:
+            times.append(dt); vals.append(res["value"])
+        last = res
+    ref.close()
+    v = float(np.mean(vals)) if vals else last["value"]
+    last["value"] = v
+    line = {"impl": "reference", "metric": "sampled negative edges/sec (D-sampling pass)", "value": v,
+            "unit": "neg_edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean(times)) if times else None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, hg, d), "cpu_baseline": last,
+            "e2e": {"value": v, "unit": "neg_edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, hg, d):
+    gen, n, deg, _ = WORKLOADS[args.workload]
+    return {"workload": "%s N=%d avg_deg=%d n_emb=%d, D-sampling pass over R=%d resident roots per GPU "
+                        "(sample_num = deg(root), Philox RNG, update_ratio=1)" % (gen, n, deg, d, args.roots),
+            "nnz": int(hg.adj.shape[0]), "max_deg": int(hg.max_deg),
+            "l2_policy": "inputs larger than L2 (embedding matrix %d MB, parent arrays %d MB)" % (
+                n * d * 4 >> 20, args.roots * n * 4 >> 20),
+            "parallelism": "roots sharded over %d GPU(s), replicated graph+embeddings" % args.gpus}
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from graphgan_b200 import graph as G, sampler as S
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    hg, emb_h, roots, d = make_inputs(args, rank)
+    dg = G.DeviceGraph(hg, dev)
+    smp = S.WalkSampler(dg)
+    emb = S.pad_embedding(emb_h, dev)
+    bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
+    t0 = time.time()
+    trees = smp.build_trees(roots)
+    torch.cuda.synchronize()
+    t_bfs = time.time() - t0
+    sample_num = dg.raw_deg[trees.roots.long()]
+    W = int(sample_num.sum().item())
+
+    # pinned host buffers of the plugin-level call
+    roots_pin = torch.from_numpy(roots.copy()).pin_memory()
+    rows_pin = [torch.empty(2 * W, dtype=torch.int32).pin_memory() for _ in range(3)]
+    nrows_pin = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+    def step(tag, e2e=False, events=None):
+        if e2e:
+            trees.roots.copy_(roots_pin, non_blocking=True)          # H2D: this step's root ids
+        if events is not None:
+            events[0].record()
+        out = smp.run(emb, bias, trees, sample_num, True, seed=args.seed, pass_tag=tag, finalize=False)
+        if events is not None:
+            events[1].record()
+        smp.finalize(out)
+        c, nb, lb, n_rows = smp.emit_d_rows(out)
+        if e2e:
+            rows_pin[0].copy_(c, non_blocking=True); rows_pin[1].copy_(nb, non_blocking=True)
+            rows_pin[2].copy_(lb, non_blocking=True); nrows_pin.copy_(n_rows, non_blocking=True)
+            torch.cuda.current_stream().synchronize()                # the caller reads the rows
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e):
+        for s in range(args.warmup):
+            step(1000 + s, e2e)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        outs = []
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start = time.time()
+        b0.record()
+        for s in range(args.steps):
+            outs.append(step(2000 + s, e2e, evs[s]))
+        b1.record()
+        barrier()
+        t_end = time.time()
+        ms = b0.elapsed_time(b1)
+        kern_ms = [a.elapsed_time(b) for a, b in evs]
+        cnts = [o.counters_host() for o in outs]
+        return ms, kern_ms, cnts, t_start, t_end
+
+    clocks = ClockSampler(local)
+    ms, kern_ms, cnts, t_start, t_end = timed(False)
+    clk = clocks.stop(t_start, t_end)
+    ms_e2e, _, cnts_e2e, _, _ = timed(True)
+
+    accepted = sum(c["accepted"] for c in cnts)
+    accepted_e2e = sum(c["accepted"] for c in cnts_e2e)
+    tot = torch.tensor([float(accepted), float(accepted_e2e)], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tot, tmax = tot.cpu().numpy(), tmax.cpu().numpy()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        # algorithmic bytes of one launch: per walk 4*ld (root row) + per candidate (4*ld + 8)
+        ld = int(emb.shape[1])
+        c0 = cnts[-1]
+        alg_bytes = float(np.mean([W * 4 * ld + c["sum_l"] * (4 * ld + 8) for c in cnts]))
+        k_ms = float(np.mean(kern_ms))
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "walk_traffic.json"))).get(args.workload)
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": "sampled negative edges/sec (D-sampling pass)", "value": float(tot[0] / (tmax[0] * 1e-3)),
+            "unit": "neg_edges/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(tmax[0] / args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, hg, d),
+            "clocks": clk,
+            "e2e": {"value": float(tot[1] / (tmax[1] * 1e-3)), "unit": "neg_edges/s",
+                    "h2d_bytes_per_step": int(roots_pin.numel() * 4),
+                    "d2h_bytes_per_step": int(3 * 2 * W * 4 + 8),
+                    "call": "WalkSampler.run + finalize + emit_d_rows with pinned host roots in / rows out"},
+            "gpu_launches": 5 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "gg::walk_kernel<4>",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "bytes_per_neg_edge": alg_bytes / max(c0["accepted"], 1),
+                         "note": "algorithmic bytes count every candidate row once per visit; hub rows are re-read "
+                                 "from L2, so achieved can exceed the HBM copy peak (see DESIGN.md section 5)"},
+            "walk": {"walks_per_step": W, "steps_per_neg_edge": c0["steps"] / max(c0["accepted"], 1),
+                     "cands_per_neg_edge": c0["sum_l"] / max(c0["accepted"], 1), "ok_roots": c0["ok_roots"],
+                     "bfs_build_s": t_bfs},
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            par_dev = trees.parent
+
+            def parent_rows(rs):   # reuse the GPU-built trees (checked against the oracle BFS in tests/)
+                idx = np.searchsorted(roots, rs)
+                return par_dev[torch.as_tensor(idx, device=dev)].cpu().numpy()
+            ref = CpuReference(hg, emb_h, roots, args.cpu_seconds, 1, parent_rows=parent_rows)
+            line["cpu_baseline"] = ref.run(args.seed)[0]
+            ref.close()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

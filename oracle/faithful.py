@@ -118,7 +118,8 @@ class Faithful:
                  trees=None):
         self.graph = graph                      # list / dict: node -> list of neighbours (raw, file order)
         self.n_node = len(graph)
-        self.E = np.asarray(emb_g, np.float64).astype(np.float32)   # tf fp32 variable (generator.py:10-14)
+        # tf fp32 variable (generator.py:10-14); an fp32 array is taken as is
+        self.E = emb_g if getattr(emb_g, "dtype", None) == np.float32 else np.asarray(emb_g, np.float64).astype(np.float32)
         self.b = np.zeros(self.n_node, np.float32) if bias_g is None else np.asarray(bias_g, np.float32)
         if emb_d is not None:
             self.Ed = np.asarray(emb_d, np.float64).astype(np.float32)

@@ -1,0 +1,210 @@
+"""GPU parity of K2 (pair score / reward / sparse gradients), K3 (TF1-style Adam), window pairs and
+the Session.run boundary against the numpy oracle (oracle/updates.py).  Floating point bar from
+BASELINE.json north_star: embedding updates within 1e-5 relative fp32."""
+import numpy as np
+import pytest
+
+from tests.golden import loader
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 2e-7
+
+
+def _batches(rs, n, n_batches, B):
+    out = []
+    for _ in range(n_batches):
+        i, j = rs.randint(0, n, B), rs.randint(0, n, B)
+        if B >= 6:
+            i[3], j[3] = i[0], j[0]   # duplicate pair
+            j[5] = i[5]               # self pair
+            i[1] = j[2]               # a row used on both sides
+        out.append((i.astype(np.int32), j.astype(np.int32)))
+    return out
+
+
+@pytest.mark.parametrize("n,d,B", [(500, 50, 64), (300, 128, 64), (200, 16, 7), (400, 256, 128), (64, 32, 1)])
+def test_discriminator_steps_match_oracle(n, d, B, cuda_device):
+    from graphgan_b200.discriminator import Discriminator
+    from oracle import updates
+    rs = np.random.RandomState(n + d)
+    emb = rs.normal(0, 0.5, size=(n, d))
+    dev_m = Discriminator(n, emb, device=cuda_device)
+    ora = updates.Discriminator(n, emb, 1e-3, 1e-5)
+    for (i, j) in _batches(rs, n, 6, B):
+        lab = (rs.random_sample(B) < 0.5).astype(np.float32)
+        assert np.allclose(dev_m.reward_pairs(i, j).cpu().numpy(), ora.reward(i, j), rtol=RTOL, atol=1e-6)
+        dev_m.d_step(i, j, lab)
+        ora.d_updates(i, j, lab)
+        assert np.allclose(dev_m.embedding_numpy(), ora.E, rtol=RTOL, atol=ATOL)
+        assert np.allclose(dev_m.bias_t.cpu().numpy(), ora.b, rtol=RTOL, atol=ATOL)
+        assert np.allclose(dev_m.m_emb[:, :d].cpu().numpy(), ora.adam.m_e, rtol=1e-4, atol=1e-9)
+        assert np.allclose(dev_m.v_emb[:, :d].cpu().numpy(), ora.adam.v_e, rtol=1e-4, atol=1e-12)
+    # padding columns stay exactly zero (they take part in the canonical dot)
+    assert float(dev_m.emb[:, d:].abs().sum()) == 0.0
+    assert int((dev_m.row_slot != -1).sum()) == 0
+
+
+@pytest.mark.parametrize("n,d,B", [(500, 50, 64), (300, 128, 33)])
+def test_generator_steps_match_oracle(n, d, B, cuda_device):
+    from graphgan_b200.generator import Generator
+    from oracle import updates
+    rs = np.random.RandomState(n * 3 + d)
+    emb = rs.normal(0, 0.5, size=(n, d))
+    dev_m = Generator(n, emb, device=cuda_device)
+    ora = updates.Generator(n, emb, 1e-3, 1e-5)
+    for (i, j) in _batches(rs, n, 6, B):
+        rew = (rs.random_sample(B) * 4).astype(np.float32)
+        dev_m.g_step(i, j, rew)
+        ora.g_updates(i, j, rew)
+        assert np.allclose(dev_m.embedding_numpy(), ora.E, rtol=RTOL, atol=ATOL)
+        assert np.allclose(dev_m.bias_t.cpu().numpy(), ora.b, rtol=RTOL, atol=ATOL)
+    assert np.allclose(dev_m.all_score_matrix().cpu().numpy(), ora.all_score(), rtol=1e-5, atol=1e-5)
+
+
+def test_generator_clip_kills_gradient(cuda_device):
+    """prob = clip(sigmoid(score), 1e-5, 1) (generator.py:26): below the clip the gradient is zero."""
+    from graphgan_b200.generator import Generator
+    n, d = 8, 32
+    emb = np.zeros((n, d)); emb[0, :] = 3.0; emb[1, :] = -3.0   # score(0,1) = -288 -> sigmoid ~ 0
+    g = Generator(n, emb, device=cuda_device)
+    before = g.embedding_numpy().copy()
+    g.g_step([0], [1], [5.0])
+    after = g.embedding_numpy()
+    # only the l2 term (lambda_gen * e) moves the rows; Adam's first step is ~lr * sign(grad)
+    assert np.allclose(np.abs(after[0] - before[0]), 1e-3, rtol=3e-2)
+    assert np.array_equal(np.sign(before[0] - after[0]), np.sign(before[0]))
+
+
+def test_session_run_boundary(cuda_device):
+    """The five sess.run call sites of graph_gan.py (154, 173, 220, 238, 298) keep their shape."""
+    from graphgan_b200.discriminator import Discriminator
+    from graphgan_b200.generator import Generator
+    from graphgan_b200.session import Session
+    from oracle import updates
+    rs = np.random.RandomState(9)
+    n, d = 120, 50
+    emb = rs.normal(0, 0.5, size=(n, d))
+    gen, dis, sess = Generator(n, emb, device=cuda_device), Discriminator(n, emb, device=cuda_device), Session()
+    og, od = updates.Generator(n, emb, 1e-3, 1e-5), updates.Discriminator(n, emb, 1e-3, 1e-5)
+    i, j = rs.randint(0, n, 64), rs.randint(0, n, 64)
+    lab = (rs.random_sample(64) < 0.5).astype(int)
+    assert sess.run(dis.d_updates, feed_dict={dis.node_id: np.array(i.tolist()), dis.node_neighbor_id: np.array(j.tolist()),
+                                              dis.label: np.array(lab.tolist())}) is None
+    od.d_updates(i, j, lab)
+    r = sess.run(dis.reward, feed_dict={dis.node_id: np.array(i), dis.node_neighbor_id: np.array(j)})
+    assert r.dtype == np.float32 and r.shape == (64,) and np.allclose(r, od.reward(i, j), rtol=RTOL, atol=1e-6)
+    sess.run(gen.g_updates, feed_dict={gen.node_id: np.array(i), gen.node_neighbor_id: np.array(j), gen.reward: r})
+    og.g_updates(i, j, r)
+    a = sess.run(gen.all_score)
+    assert a.shape == (n, n) and np.allclose(a, og.all_score(), rtol=1e-5, atol=1e-5)
+    e = sess.run(dis.embedding_matrix)
+    assert e.shape == (n, d) and np.allclose(e, od.E, rtol=RTOL, atol=ATOL)
+    assert np.allclose(sess.run(gen.embedding_matrix), og.E, rtol=RTOL, atol=ATOL)
+    with pytest.raises(ValueError):
+        sess.run(dis.d_updates, feed_dict={dis.node_id: i})
+    # compatibility fetches
+    s = sess.run(gen.score, feed_dict={gen.node_id: i, gen.node_neighbor_id: j})
+    assert np.allclose(s, og.score(i, j), rtol=1e-5, atol=1e-5)
+    L = sess.run(dis.loss, feed_dict={dis.node_id: i, dis.node_neighbor_id: j, dis.label: lab.astype(np.float32)})
+    assert abs(L - od.loss(i, j, lab)) < 1e-3 * max(1.0, abs(L))
+
+
+def test_window_pairs_match_reference_vectors(cuda_device):
+    import ctypes as C
+    import torch
+    from graphgan_b200 import _cabi
+    c = loader.load("tiny")
+    pp, pf, op, of = c.win_paths_ptr, c.win_paths_flat, c.win_pairs_ptr, c.win_pairs_flat
+    paths_l = [pf[pp[k]:pp[k + 1]].tolist() for k in range(pp.shape[0] - 1)] + [[1, 0, 2, 4, 2], [], [5]]
+    W, mp = len(paths_l), 16
+    paths = np.full((W, mp), -1, np.int32)
+    plen = np.zeros(W, np.int32)
+    for k, p in enumerate(paths_l):
+        paths[k, :len(p)] = p; plen[k] = len(p)
+    lib = _cabi.lib()
+    dp, dl = torch.as_tensor(paths).to(cuda_device), torch.as_tensor(plen).to(cuda_device)
+    ptr_t = torch.zeros(W + 1, dtype=torch.int64, device=cuda_device)
+    tot = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    n1 = torch.zeros(4096, dtype=torch.int32, device=cuda_device); n2 = torch.zeros_like(n1)
+    _cabi.check(lib.gg_window_pairs(W, dp.data_ptr(), dl.data_ptr(), mp, 2, ptr_t.data_ptr(), n1.data_ptr(), n2.data_ptr(),
+                                    tot.data_ptr(), 4096, 0), "gg_window_pairs")
+    torch.cuda.synchronize()
+    from oracle import faithful
+    want = [pr for p in paths_l for pr in (faithful.node_pairs_from_path(p, 2) if len(p) else [])]
+    m = int(tot.item())
+    assert m == len(want)
+    got = np.stack([n1[:m].cpu().numpy(), n2[:m].cpu().numpy()], 1).tolist()
+    assert got == want
+    # the reference's own docstring vector (graph_gan.py:276-277) sits at index W-3
+    k = W - 3
+    o = ptr_t.cpu().numpy()
+    assert got[o[k]:o[k + 1]] == [[1, 0], [1, 2], [0, 1], [0, 2], [0, 4], [2, 1], [2, 0], [2, 4], [4, 0], [4, 2]]
+    # reference-recorded pairs for the 64 random paths
+    for q in range(pp.shape[0] - 1):
+        assert [x for pr in got[o[q]:o[q + 1]] for x in pr] == of[op[q]:op[q + 1]].tolist()
+
+
+def test_trainer_epoch_on_cagrqc(cuda_device, tmp_path, monkeypatch):
+    """Config C1 end to end through the re-hosted GraphGAN class: the G-pass pair list and rewards
+    equal the canonical oracle's, one epoch of updates runs, embeddings/eval files appear."""
+    import torch
+    from graphgan_b200 import config, graph as G
+    from graphgan_b200.graph_gan import GraphGAN
+    from oracle import canonical as can, faithful, updates
+    c = loader.load("cagrqc")
+    monkeypatch.setattr(config, "n_emb", 50)
+    monkeypatch.setattr(config, "n_epochs", 1)
+    monkeypatch.setattr(config, "n_epochs_dis", 1); monkeypatch.setattr(config, "dis_interval", 1)
+    monkeypatch.setattr(config, "n_epochs_gen", 1); monkeypatch.setattr(config, "gen_interval", 1)
+    monkeypatch.setattr(config, "n_sample_gen", 2)
+    monkeypatch.setattr(config, "device", str(cuda_device))
+    monkeypatch.setattr(config, "seed", 5)
+    # files in the reference formats
+    def wr(name, e):
+        p = tmp_path / name
+        p.write_text("".join("%d\t%d\n" % (a, b) for a, b in e))
+        return str(p)
+    monkeypatch.setattr(config, "test_filename", wr("test.txt", c.test_edges))
+    monkeypatch.setattr(config, "test_neg_filename", wr("test_neg.txt", c.test_neg_edges))
+    monkeypatch.setattr(config, "emb_filenames", [str(tmp_path / "gen.emb"), str(tmp_path / "dis.emb")])
+    monkeypatch.setattr(config, "result_filename", str(tmp_path / "res.txt"))
+    monkeypatch.setattr(config, "model_log", str(tmp_path / "log") + "/")
+    hg = G.HostGraph(c.train_edges, c.test_edges)
+    gan = GraphGAN(host_graph=hg, node_embed_init_d=c.emb_d, node_embed_init_g=c.emb_g)
+    assert gan.n_node == 5242 and gan.trees is not None
+    # epoch-0 quality line of the shipped pretrain embeddings (0.7598...)
+    gan.write_embeddings_to_file()
+    res = GraphGAN.evaluation(gan)
+    assert abs(float(res[0].split(":")[1]) - 0.7598343685300207) < 2e-3
+    # D pass vs canonical oracle
+    ce, ne, la = gan.prepare_data_for_d()
+    roots = np.arange(5242, dtype=np.int32)
+    par = gan.trees.parent.cpu().numpy()
+    bits = np.zeros(gan.device_graph.n_bit_words, np.uint32)
+    E = can.pad_rows(c.emb_g)
+    ref = can.walk_pass(E, np.zeros(5242, np.float32), hg.indptr, hg.adj, roots, par, hg.degrees(), True, bits, seed=5, pass_tag=1)
+    rc, rn, rl = can.d_rows(ref, roots, hg.raw_indptr, hg.raw_adj)
+    assert np.array_equal(ce.cpu().numpy(), rc) and np.array_equal(ne.cpu().numpy(), rn)
+    assert np.array_equal(la.cpu().numpy(), rl.astype(np.float32))
+    # G pass: pairs + rewards
+    n1, n2, rw = gan.prepare_data_for_g()
+    ref_g = can.walk_pass(E, np.zeros(5242, np.float32), hg.indptr, hg.adj, roots, par, np.full(5242, 2), False, bits,
+                          seed=5, pass_tag=2, max_path=64)
+    w1, w2 = [], []
+    for p in can.paths_list(ref_g):
+        for a, b in faithful.node_pairs_from_path(p, 2):
+            w1.append(a); w2.append(b)
+    assert np.array_equal(n1.cpu().numpy(), np.asarray(w1, np.int32)) and np.array_equal(n2.cpu().numpy(), np.asarray(w2, np.int32))
+    od = updates.Discriminator(5242, c.emb_d, 1e-3, 1e-5)
+    assert np.allclose(rw.cpu().numpy(), od.reward(w1, w2), rtol=1e-5, atol=1e-6)
+    # a short training run end to end, checkpoint round trip
+    gan.train()
+    assert (tmp_path / "gen.emb").exists() and (tmp_path / "res.txt").read_text().count("gen:") == 3
+    gan.save(str(tmp_path / "ck.pt"))
+    e0 = gan.generator.embedding_numpy().copy()
+    gan.generator.emb.zero_()
+    gan.load(str(tmp_path / "ck.pt"))
+    assert np.array_equal(gan.generator.embedding_numpy(), e0)
+    assert gan.get_node_pairs_from_path([1, 0, 2, 4, 2]) == [[1, 0], [1, 2], [0, 1], [0, 2], [0, 4], [2, 1], [2, 0], [2, 4], [4, 0], [4, 2]]
+    s, p = gan.sample(0, None, 3, for_d=False)
+    assert s is None or (len(s) == 3 and all(q[-1] == q[-3] for q in p))

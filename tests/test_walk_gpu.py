@@ -16,7 +16,7 @@ def _setup(case, cuda_device, roots=None):
     from graphgan_b200 import graph as G, sampler as S
     from oracle import canonical as can
     edges = case["train_edges"]
-    hg = G.HostGraph(edges, case["test_edges"])
+    hg = G.HostGraph(edges, case["test_edges"], n_node=case.n)
     assert hg.n_node == case.n
     # host graph == the reference reader's graph (utils.py:12-47)
     ptr, flat = can.raw_csr(case.graph)
@@ -147,8 +147,8 @@ def test_hub_lists_use_global_scratch(cuda_device):
     """A power-law graph whose hub has > SMEM_CAP neighbours: the long-list (global scratch) path
     and multi-tile softmax must agree bit-for-bit with the oracle as well."""
     from graphgan_b200 import synth
-    n, d = 6000, 128
-    edges = synth.power_law(n, 16, seed=3)
+    n, d = 12000, 128
+    edges = synth.power_law(n, 20, seed=3)
     case = loader.Case(n=n, dim=d, train_edges=edges, test_edges=np.zeros((0, 2), np.int64),
                        emb_g=synth.embeddings(n, d, seed=5, sigma=0.3), bias_g=np.zeros(n, np.float32))
     from graphgan_b200 import graph as G
