@@ -28,6 +28,8 @@ class WalkDesc(C.Structure):
         ("samples", C.c_void_p), ("status", C.c_void_p), ("first_edge", C.c_void_p), ("wsteps", C.c_void_p),
         ("wsuml", C.c_void_p), ("paths", C.c_void_p), ("path_len", C.c_void_p), ("counters", C.c_void_p),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64), ("work_counter", C.c_void_p),
+        ("edge_score", C.c_void_p), ("root_q", C.c_void_p), ("rq_ptr", C.c_void_p),
+        ("hub_threshold", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -36,6 +38,8 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "gg_last_error": (C.c_char_p, []),
     "gg_abi_version": (C.c_int, []),
+    "gg_hub_scores": (C.c_int, [_I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P]),
+    "gg_root_cdf": (C.c_int, [C.POINTER(WalkDesc), _P, _P, _P]),
     "gg_walk_scratch_bytes": (C.c_int, [_I32, C.POINTER(_I64)]),
     "gg_walk_sample": (C.c_int, [C.POINTER(WalkDesc), _P]),
     "gg_walk_finalize": (C.c_int, [_I64, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -44,7 +48,9 @@ SIGNATURES = {
     "gg_bfs_build": (C.c_int, [_I64, _P, _P, _I64, _P, _P, _P, _I64, _P]),
     "gg_pair_reward": (C.c_int, [_I64, _P, _P, _P, _P, _I32, _P, _P]),
     "gg_all_score": (C.c_int, [_I64, _P, _P, _I32, _P, _P]),
-    "gg_pair_grad": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P]),
+    "gg_pair_grad": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P]),
+    "gg_grad_buf_floats": (_I64, [_I32, _I32]),
+    "gg_grad_merge": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "gg_adam_apply": (C.c_int, [_I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),
     "gg_window_pairs": (C.c_int, [_I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _P]),
 }

@@ -35,10 +35,11 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n_node, int ld, flo
             float4 m = *reinterpret_cast<float4 *>(m_emb + ro + c);
             float4 v = *reinterpret_cast<float4 *>(v_emb + ro + c);
             float4 x = *reinterpret_cast<float4 *>(emb + ro + c);
-#define GG_ADAM1(f)                                        \
-    m.f = m.f * b1 + omb1 * g.f;                           \
-    v.f = v.f * b2 + omb2 * (g.f * g.f);                   \
-    x.f = x.f - lr_t * m.f / (sqrtf(v.f) + eps);
+// TF1.8 op order (assign m*b1; scatter_add (1-b1)*g; ... var -= lr*m/(sqrt(v)+eps)), no contraction
+#define GG_ADAM1(f)                                                                                   \
+    m.f = __fadd_rn(__fmul_rn(m.f, b1), __fmul_rn(omb1, g.f));                                        \
+    v.f = __fadd_rn(__fmul_rn(v.f, b2), __fmul_rn(__fmul_rn(omb2, g.f), g.f));                        \
+    x.f = __fsub_rn(x.f, __fdiv_rn(__fmul_rn(lr_t, m.f), __fadd_rn(__fsqrt_rn(v.f), eps)));
             GG_ADAM1(x) GG_ADAM1(y) GG_ADAM1(z) GG_ADAM1(w)
 #undef GG_ADAM1
             *reinterpret_cast<float4 *>(m_emb + ro + c) = m;
@@ -47,10 +48,10 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n_node, int ld, flo
         }
         if (lane == 0) {
             const float g = slot >= 0 ? grad_bias[slot] : 0.0f;
-            const float m = m_bias[row] * b1 + omb1 * g;
-            const float v = v_bias[row] * b2 + omb2 * (g * g);
+            const float m = __fadd_rn(__fmul_rn(m_bias[row], b1), __fmul_rn(omb1, g));
+            const float v = __fadd_rn(__fmul_rn(v_bias[row], b2), __fmul_rn(__fmul_rn(omb2, g), g));
             m_bias[row] = m; v_bias[row] = v;
-            bias[row] = bias[row] - lr_t * m / (sqrtf(v) + eps);
+            bias[row] = __fsub_rn(bias[row], __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(__fsqrt_rn(v), eps)));
             if (slot >= 0) row_slot[row] = -1;
         }
     }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) all_score_kernel(long long n, const float
 constexpr int GRAD_THREADS = 1024;
 
 __global__ void __launch_bounds__(GRAD_THREADS, 1)
-pair_grad_kernel(int mode, int B, const int *__restrict__ ni, const int *__restrict__ nj, const float *__restrict__ aux,
+pair_grad_kernel(int mode, int B, int batch_total, const int *__restrict__ ni, const int *__restrict__ nj, const float *__restrict__ aux,
                  const float *__restrict__ emb, const float *__restrict__ bias, int ld, float lambda,
                  int *__restrict__ n_unique, int *__restrict__ uniq_ids, float *__restrict__ grad_rows,
                  float *__restrict__ grad_bias, int *__restrict__ row_slot) {
@@ -80,13 +80,13 @@ pair_grad_kernel(int mode, int B, const int *__restrict__ ni, const int *__restr
         float s = group_dot(emb + (size_t)i * ld, emb + (size_t)j * ld, ld, g);
         if (valid && g == 0) {
             s = __fadd_rn(s, bias[j]);
-            const float p = 1.0f / (1.0f + expf(-s));   // sigmoid
+            const float p = (float)(1.0 / (1.0 + exp(-(double)s)));   // sigmoid (B values: fp64 costs nothing)
             float d;
             if (mode == 0) {
                 d = p - aux[k];                          // d/ds sigmoid_xent(label, s) = sigmoid(s) - label
             } else {
                 // d/ds [-(1/B) r log(clip(p,1e-5,1))] = -(r/B)(1-p) where the clip passes (p >= 1e-5)
-                d = (p >= 1e-5f) ? -(aux[k] / (float)B) * (1.0f - p) : 0.0f;
+                d = (p >= 1e-5f) ? -(aux[k] / (float)batch_total) * (1.0f - p) : 0.0f;
             }
             delta[k] = d;
         }
@@ -147,11 +147,12 @@ pair_grad_kernel(int mode, int B, const int *__restrict__ ni, const int *__restr
                 const int other = (t < B) ? nj[k] : ni[k];
                 const float4 o = ldg4(emb + (size_t)other * ld + c);
                 const float d = delta[k];
-                // d(score)/d(this row) = other row;  l2 term: lambda * this row, once per occurrence
-                acc.x += d * o.x + lambda * self.x;
-                acc.y += d * o.y + lambda * self.y;
-                acc.z += d * o.z + lambda * self.z;
-                acc.w += d * o.w + lambda * self.w;
+                // d(score)/d(this row) = other row;  l2 term: lambda * this row, once per occurrence.
+                // Explicit mul/mul/add/add (no fma contraction): the same op sequence as the IndexedSlices
+                // sum of the numpy oracle, so cancellation noise in near-zero coordinates stays comparable.
+#define GG_ACC(f) acc.f = __fadd_rn(acc.f, __fadd_rn(__fmul_rn(d, o.f), __fmul_rn(lambda, self.f)))
+                GG_ACC(x); GG_ACC(y); GG_ACC(z); GG_ACC(w);
+#undef GG_ACC
             }
             *reinterpret_cast<float4 *>(grad_rows + (size_t)u * ld + c) = acc;
         }
@@ -160,8 +161,92 @@ pair_grad_kernel(int mode, int B, const int *__restrict__ ni, const int *__restr
             const float bself = bias[row];
             for (int t = B; t < E; ++t) {
                 if (slot[t] != u) continue;
-                gb += delta[t - B] + (mode == 0 ? lambda * bself : 0.0f);  // generator.py:28-29 has no bias l2
+                gb = __fadd_rn(gb, mode == 0 ? __fadd_rn(delta[t - B], __fmul_rn(lambda, bself)) : delta[t - B]);  // generator.py:28-29: no bias l2
             }
+            grad_bias[u] = gb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- data-parallel merge (1 CTA)
+// Entry (r, s) = slot s of rank r's compact gradient.  Same unique + ordered segment-sum as above, on
+// ready-made row vectors; entry order is rank-major, so all ranks reduce in the same order.
+__global__ void __launch_bounds__(GRAD_THREADS, 1)
+grad_merge_kernel(int world, int cap, int ld, const float *__restrict__ gathered, int *__restrict__ n_unique,
+                  int *__restrict__ uniq_ids, float *__restrict__ grad_rows, float *__restrict__ grad_bias,
+                  int *__restrict__ row_slot) {
+    extern __shared__ int smem[];
+    const int E = world * cap;
+    int *ids = smem;          // [E] row id or -1
+    int *slot = ids + E;      // [E]
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t stride = (size_t)cap * ld + 2 * (size_t)cap + 4;   // == gg_grad_buf_floats
+    for (int t = tid; t < E; t += GRAD_THREADS) {
+        const int r = t / cap, sidx = t % cap;
+        const float *buf = gathered + (size_t)r * stride;
+        const int nu = __float_as_int(buf[(size_t)cap * ld + 2 * (size_t)cap]);
+        const int id = (sidx < nu) ? __float_as_int(buf[(size_t)cap * ld + cap + sidx]) : -1;
+        ids[t] = id;
+        if (id >= 0) row_slot[id] = -1;   // forget the slots of the local (pre-merge) gradient
+    }
+    __syncthreads();
+    int base_total = 0;
+    for (int t0 = 0; t0 < E; t0 += GRAD_THREADS) {
+        const int t = t0 + tid;
+        int is_first = 0, first_t = t;
+        if (t < E && ids[t] >= 0) {
+            const int id = ids[t];
+            int f = t;
+            for (int q = 0; q < t; ++q) if (ids[q] == id) { f = q; break; }
+            first_t = f; is_first = (f == t);
+        }
+        int x = is_first;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int v = s_warp[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(FULL, v, off);
+                if (lane >= off) v += y;
+            }
+            s_warp[lane] = v;
+        }
+        __syncthreads();
+        const int excl = base_total + (wid ? s_warp[wid - 1] : 0) + x - is_first;
+        if (t < E) slot[t] = (ids[t] < 0) ? -(E + 1) : (is_first ? excl : -1 - first_t);
+        if (t < E && is_first) { uniq_ids[excl] = ids[t]; row_slot[ids[t]] = excl; }
+        base_total += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) { s_total = base_total; *n_unique = base_total; }
+    __syncthreads();
+    for (int t = tid; t < E; t += GRAD_THREADS)
+        if (slot[t] < 0 && slot[t] != -(E + 1)) slot[t] = slot[-1 - slot[t]];
+    __syncthreads();
+    const int U = s_total;
+    for (int u = wid; u < U; u += GRAD_THREADS / 32) {
+        for (int c = 4 * lane; c < ld; c += 128) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = 0; t < E; ++t) {
+                if (slot[t] != u) continue;
+                const float4 o = *reinterpret_cast<const float4 *>(gathered + (size_t)(t / cap) * stride + (size_t)(t % cap) * ld + c);
+                acc.x = __fadd_rn(acc.x, o.x); acc.y = __fadd_rn(acc.y, o.y);
+                acc.z = __fadd_rn(acc.z, o.z); acc.w = __fadd_rn(acc.w, o.w);
+            }
+            *reinterpret_cast<float4 *>(grad_rows + (size_t)u * ld + c) = acc;
+        }
+        if (lane == 0) {
+            float gb = 0.0f;
+            for (int t = 0; t < E; ++t)
+                if (slot[t] == u) gb = __fadd_rn(gb, gathered[(size_t)(t / cap) * stride + (size_t)cap * ld + (t % cap)]);
             grad_bias[u] = gb;
         }
     }
@@ -233,7 +318,7 @@ extern "C" int gg_all_score(int64_t n_node, const float *emb, const float *bias,
     return gg::check_cuda(cudaGetLastError(), "all_score kernel launch");
 }
 
-extern "C" int gg_pair_grad(int32_t mode, int32_t n_pairs, const int32_t *node_id, const int32_t *node_neighbor_id,
+extern "C" int gg_pair_grad(int32_t mode, int32_t n_pairs, int32_t batch_total, const int32_t *node_id, const int32_t *node_neighbor_id,
                             const float *aux, const float *emb, const float *bias, int32_t ld, float lambda,
                             int32_t *n_unique, int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot,
                             void *stream) {
@@ -244,9 +329,25 @@ extern "C" int gg_pair_grad(int32_t mode, int32_t n_pairs, const int32_t *node_i
     GG_REQUIRE(ld > 0 && ld % 32 == 0, "ld must be a positive multiple of 32");
     const size_t smem = (size_t)n_pairs * (2 + 2 + 1) * 4;
     gg::pair_grad_kernel<<<1, gg::GRAD_THREADS, smem, (cudaStream_t)stream>>>(
-        mode, n_pairs, node_id, node_neighbor_id, aux, emb, bias, ld, lambda, n_unique, uniq_ids, grad_rows, grad_bias,
-        row_slot);
+        mode, n_pairs, batch_total > 0 ? batch_total : n_pairs, node_id, node_neighbor_id, aux, emb, bias, ld, lambda,
+        n_unique, uniq_ids, grad_rows, grad_bias, row_slot);
     return gg::check_cuda(cudaGetLastError(), "pair_grad kernel launch");
+}
+
+extern "C" int64_t gg_grad_buf_floats(int32_t cap, int32_t ld) { return (int64_t)cap * ld + 2 * (int64_t)cap + 4; }
+
+extern "C" int gg_grad_merge(int32_t world, int32_t cap, int32_t ld, const float *gathered, int32_t *n_unique,
+                             int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot, void *stream) {
+    GG_REQUIRE(world > 0 && cap > 0 && (int64_t)world * cap <= 2 * GG_MAX_BATCH * 8, "too many entries to merge");
+    GG_REQUIRE(gathered && n_unique && uniq_ids && grad_rows && grad_bias && row_slot, "null pointer");
+    GG_REQUIRE(ld > 0 && ld % 32 == 0, "ld must be a positive multiple of 32");
+    const size_t smem = (size_t)world * cap * 2 * 4;
+    GG_REQUIRE(smem <= 200 * 1024, "merge exceeds shared memory");
+    if (smem > 48 * 1024)
+        GG_CHECK(cudaFuncSetAttribute(gg::grad_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gg::grad_merge_kernel<<<1, gg::GRAD_THREADS, smem, (cudaStream_t)stream>>>(world, cap, ld, gathered, n_unique, uniq_ids,
+                                                                             grad_rows, grad_bias, row_slot);
+    return gg::check_cuda(cudaGetLastError(), "grad merge launch");
 }
 
 extern "C" int gg_window_pairs(int64_t n_walks, const int32_t *paths, const int32_t *path_len, int32_t max_path,

@@ -12,17 +12,10 @@
 //   3. softmax (utils.py:131-133) + float64 CDF + inverse-CDF draw (numpy legacy
 //      RandomState.choice, called at graph_gan.py:262) with warp shuffles.
 // The arithmetic is the canonical sequence of DESIGN.md section 3 == oracle/gg_oracle.c.
-#include "gg_common.cuh"
+#include "walk_common.cuh"
 
 namespace gg {
 namespace {
-
-constexpr int WARPS_PER_CTA = 8;
-constexpr int SMEM_CAP = 320;  // candidates per warp kept in shared memory (ids + scores)
-
-struct WalkCtx {
-    gg_walk_desc d;
-};
 
 struct Rng {
     int mode;
@@ -42,47 +35,12 @@ struct Rng {
     }
 };
 
-// softmax + CDF + draw over sc[0..n) (canonical; == ggo_choose).  All lanes return idx.
-__device__ __forceinline__ int choose_index(float *sc, int n, double u, int lane) {
-    float m = -INFINITY;
-    for (int i = lane; i < n; i += 32) m = fmaxf(m, sc[i]);
-    m = warp_max(m);
-    float S = 0.0f;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-        const int i = t0 + lane;
-        float e = 0.0f;
-        if (i < n) { e = exp_c(__fsub_rn(sc[i], m)); sc[i] = e; }
-        const float T = warp_sum_butterfly(e);
-        S = (t0 == 0) ? T : __fadd_rn(S, T);
-    }
-    __syncwarp();
-    double total = 0.0;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-        const int i = t0 + lane;
-        double x = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;
-        x = warp_scan_ks(x, lane);
-        total = __dadd_rn(total, __shfl_sync(FULL, x, 31));
-    }
-    double carry = 0.0;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-        const int i = t0 + lane;
-        double x = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;
-        x = warp_scan_ks(x, lane);
-        const double q = __ddiv_rn(__dadd_rn(carry, x), total);
-        const unsigned hit = __ballot_sync(FULL, (i < n) && (q > u));
-        if (hit) return t0 + __ffs(hit) - 1;
-        carry = __dadd_rn(carry, __shfl_sync(FULL, x, 31));
-    }
-    return n - 1;
-}
-
 // One complete walk, executed by a full warp.  Returns the status.
 template <int CPL>
 __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slot, uint32_t k, long long w,
                                         int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
                                         unsigned long long &raw_steps, unsigned long long &raw_suml,
-                                        unsigned long long &overflow) {
-    const int grp = lane >> 3, g = lane & 7;
+                                        unsigned long long &overflow, unsigned long long &rows_gathered) {
     const int root = d.roots[slot];
     const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
     const int ld = d.ld;
@@ -93,67 +51,61 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
     plen = 1;
 
     for (;;) {
-        // ---- candidate list (graph_gan.py:250-259)
-        bool inc_father = step > 0;
-        if (d.for_d && step == 1) inc_father = false;
-        if (!d.for_d && step == 1 && ((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u)) inc_father = false;
         const long long a0 = d.indptr[cur], a1 = d.indptr[cur + 1];
-        const bool in_smem = (a1 - a0 + 1) <= SMEM_CAP;
-        int *ids = in_smem ? s_ids : g_ids;
-        float *sc = in_smem ? s_sc : g_sc;
-        int n = 0;
-        if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
-        for (long long e0 = a0; e0 < a1; e0 += 32) {
-            const long long e = e0 + lane;
-            int v = -1;
-            if (e < a1) v = __ldg(d.adj + e);
-            const bool isc = (v >= 0) && (__ldg(par + v) == cur);
-            const unsigned mk = __ballot_sync(FULL, isc);
-            if (isc) ids[n + __popc(mk & ((1u << lane) - 1u))] = v;
-            n += __popc(mk);
-        }
-        __syncwarp();
-        if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
-
-        // ---- scores: all_score[cur, cand] (generator.py:21), canonical dot
-        float4 c4[CPL];
-        {
-            const float *crow = d.emb + (size_t)cur * (size_t)ld + 4 * g;
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) c4[c] = ldg4(crow + 32 * c);
-        }
-        for (int i0 = 0; i0 < n; i0 += 8) {
-            const int ia = i0 + grp, ib = i0 + 4 + grp;
-            const bool va = ia < n, vb = ib < n;
-            const int ca = va ? ids[ia] : cur, cb = vb ? ids[ib] : cur;
-            const float *ra = d.emb + (size_t)ca * (size_t)ld + 4 * g;
-            const float *rb = d.emb + (size_t)cb * (size_t)ld + 4 * g;
-            float4 xa[CPL], xb[CPL];
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) xa[c] = ldg4(ra + 32 * c);
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) xb[c] = ldg4(rb + 32 * c);
-            const float ba = __ldg(d.bias + ca), bb = __ldg(d.bias + cb);
-            float sa = 0.0f, sb = 0.0f;
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) sa = fma4(c4[c], xa[c], sa);
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) sb = fma4(c4[c], xb[c], sb);
-            sa = group8_sum(sa);
-            sb = group8_sum(sb);
-            if (g == 0) {
-                if (va) sc[ia] = __fadd_rn(sa, ba);
-                if (vb) sc[ib] = __fadd_rn(sb, bb);
+        int n, idx, nxt;
+        bool inc_father = false;
+        if (step == 0 && d.root_q) {
+            // ---- root step from the per-root CDF (hub.cu: root_cdf_kernel): every walk of a root
+            // sees the same candidate list tree[root][1:] and the same scores, so the softmax/CDF
+            // is computed once per root per pass and each walk only inverts it.
+            n = (int)(a1 - a0);
+            if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-253
+            const double u = rng.draw((uint32_t)root, k, 0u);
+            if (rng.exhausted) { status = GG_NOTRUN; break; }
+            idx = cdf_search(d.root_q + __ldg(d.rq_ptr + slot), n, u);
+            nxt = __ldg(d.adj + a0 + idx);
+        } else {
+            // ---- candidate list (graph_gan.py:250-259)
+            inc_father = step > 0;
+            if (d.for_d && step == 1) inc_father = false;
+            if (!d.for_d && step == 1 && ((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u)) inc_father = false;
+            const bool in_smem = (a1 - a0 + 1) <= SMEM_CAP;
+            const bool cached = d.edge_score && (a1 - a0) >= d.hub_threshold;  // scores precomputed per pass
+            int *ids = in_smem ? s_ids : g_ids;
+            float *sc = in_smem ? s_sc : g_sc;
+            n = 0;
+            if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
+            for (long long e0 = a0; e0 < a1; e0 += 32) {
+                const long long e = e0 + lane;
+                int v = -1;
+                if (e < a1) v = __ldg(d.adj + e);
+                const bool isc = (v >= 0) && (__ldg(par + v) == cur);
+                const unsigned mk = __ballot_sync(FULL, isc);
+                if (isc) {
+                    const int pos = n + __popc(mk & ((1u << lane) - 1u));
+                    ids[pos] = v;
+                    if (cached) sc[pos] = __ldg(d.edge_score + e);
+                }
+                n += __popc(mk);
             }
-        }
-        __syncwarp();
+            __syncwarp();
+            if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
 
-        // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
-        const double u = rng.draw((uint32_t)root, k, (uint32_t)step);
-        if (rng.exhausted) { status = GG_NOTRUN; break; }
-        const int idx = choose_index(sc, n, u, lane);
-        const int nxt = ids[idx];
-        __syncwarp();
+            // ---- scores: all_score[cur, cand] (generator.py:21), canonical dot
+            if (!cached || inc_father) {
+                float4 c4[CPL];
+                load_row<CPL>(d.emb, ld, cur, lane & 7, c4);
+                score_list<CPL>(d.emb, d.bias, ld, c4, ids, sc, cached ? 1 : n, cur, lane);
+                rows_gathered += 1u + (unsigned)(cached ? 1 : n);
+            }
+
+            // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
+            const double u = rng.draw((uint32_t)root, k, (uint32_t)step);
+            if (rng.exhausted) { status = GG_NOTRUN; break; }
+            idx = choose_index(sc, n, u, lane);
+            nxt = ids[idx];
+            __syncwarp();
+        }
         if (step == 0) fedge = (int)(a0 + idx);  // every walk-CSR neighbour of the root is its child
         if (prow && lane == 0 && plen < d.max_path) prow[plen] = nxt;
         ++plen;
@@ -186,7 +138,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_kernel(const __grid_c
     Rng rng;
     rng.mode = GG_RNG_PHILOX; rng.k0 = (uint32_t)d.seed; rng.k1 = (uint32_t)(d.seed >> 32); rng.tag = d.pass_tag;
     rng.stream = nullptr; rng.n_stream = 0; rng.cursor = 0; rng.exhausted = 0;
-    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0;
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
     const bool ratio_all = d.update_ratio >= 1.0;
 
     for (;;) {
@@ -214,12 +166,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_kernel(const __grid_c
                 continue;
             }
         }
-        walk_one<CPL>(d, rng, slot, k, w, s_ids[wid], s_sc[wid], g_ids, g_sc, lane, raw_steps, raw_suml, overflow);
+        walk_one<CPL>(d, rng, slot, k, w, s_ids[wid], s_sc[wid], g_ids, g_sc, lane, raw_steps, raw_suml, overflow,
+                      rows_gathered);
     }
     if (lane == 0) {
         if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
         if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
         if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
+        if (rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
     }
 }
 
@@ -236,7 +190,7 @@ __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__
     Rng rng;
     rng.mode = GG_RNG_STREAM; rng.k0 = rng.k1 = rng.tag = 0;
     rng.stream = d.stream; rng.n_stream = d.n_stream; rng.cursor = 0; rng.exhausted = 0;
-    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0;
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
     for (long long slot = 0; slot < d.n_roots && !rng.exhausted; ++slot) {
         const long long w0 = d.walk_ptr[slot], w1 = d.walk_ptr[slot + 1];
         const double ur = rng.draw(0, 0, 0);
@@ -252,7 +206,7 @@ __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__
                 continue;
             }
             const int st = walk_one<CPL>(d, rng, (int)slot, (uint32_t)(w - w0), w, s_ids, s_sc, g_ids, g_sc, lane,
-                                         raw_steps, raw_suml, overflow);
+                                         raw_steps, raw_suml, overflow, rows_gathered);
             if (st != GG_DONE) dead = true;
         }
     }
@@ -260,6 +214,7 @@ __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__
         atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
         atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
         atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
+        atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
         d.counters[GG_CNT_STREAM_USED] = (unsigned long long)rng.cursor + (rng.exhausted ? (1ull << 62) : 0ull);
     }
 }
@@ -355,6 +310,8 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
     GG_REQUIRE(d.for_d || d.d1_bits, "G mode needs d1_bits");
     GG_REQUIRE(d.n_walks < (1ll << 32), "too many walks in one call");
     GG_REQUIRE(d.max_cand > 0 && d.scratch, "scratch missing");
+    GG_REQUIRE(!d.root_q || d.rq_ptr, "root_q needs rq_ptr");
+    GG_REQUIRE(!d.edge_score || (d.hub_threshold > 0 && d.hub_threshold < gg::SMEM_CAP), "hub_threshold out of range");
     cudaStream_t st = (cudaStream_t)stream;
     GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));
     if (d.n_walks == 0 || d.n_roots == 0) return 0;

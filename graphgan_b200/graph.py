@@ -90,6 +90,25 @@ class DeviceGraph:
         self.n_bit_words = (host.adj.shape[0] + 31) // 32 + 1
         self.d1_bits = torch.zeros(self.n_bit_words, dtype=torch.int32, device=self.device)
 
+    def hub_tiles(self, threshold, tile_edges=256):
+        """Work list of gg_hub_scores: (node, first entry) of every `tile_edges`-entry slice of the
+        adjacency of nodes whose walk-CSR degree is >= threshold.  Static per graph; cached."""
+        import torch
+        key = (int(threshold), int(tile_edges))
+        if getattr(self, "_hub_key", None) != key:
+            deg = np.diff(self.host.indptr)
+            hubs = np.flatnonzero(deg >= threshold)
+            nt = (deg[hubs] + tile_edges - 1) // tile_edges
+            node = np.repeat(hubs, nt).astype(np.int32)
+            first = np.repeat(np.cumsum(nt) - nt, nt)
+            begin = (self.host.indptr[node] + (np.arange(node.shape[0]) - first) * tile_edges).astype(np.int64)
+            self._hub_key = key
+            self._hub = (torch.from_numpy(node).to(self.device), torch.from_numpy(begin).to(self.device),
+                         int(node.shape[0]), int(deg[hubs].sum()))
+            if not hasattr(self, "edge_score"):
+                self.edge_score = torch.empty(max(self.host.adj.shape[0], 1), dtype=torch.float32, device=self.device)
+        return self._hub
+
     def reset_tree_mutations(self):
         """Forget every father removal (== reloading the reference's tree cache)."""
         self.d1_bits.zero_()

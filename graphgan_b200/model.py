@@ -92,7 +92,7 @@ class PairModel:
         if B > MAX_BATCH:
             raise ValueError("batch of %d pairs exceeds GG_MAX_BATCH=%d" % (B, MAX_BATCH))
         st = self._stream()
-        _cabi.check(self.lib.gg_pair_grad(self._step_mode, B, ptr(i), ptr(j), ptr(a), ptr(self.emb), ptr(self.bias_t),
+        _cabi.check(self.lib.gg_pair_grad(self._step_mode, B, 0, ptr(i), ptr(j), ptr(a), ptr(self.emb), ptr(self.bias_t),
                                           self.ld, C.c_float(float(self.lam)), ptr(self.n_unique), ptr(self.uniq_ids),
                                           ptr(self.grad_rows), ptr(self.grad_bias), ptr(self.row_slot), st),
                     "gg_pair_grad")

@@ -14,7 +14,8 @@ from ._cabi import ptr
 
 RNG_PHILOX, RNG_STREAM = 0, 1
 NOTRUN, DONE, VOID, SKIPPED = 0, 1, 2, 3
-CNT = dict(steps=0, sum_l=1, accepted=2, ok_roots=3, path_overflow=4, raw_steps=5, raw_sum_l=6, stream_used=7)
+CNT = dict(steps=0, sum_l=1, accepted=2, ok_roots=3, path_overflow=4, raw_steps=5, raw_sum_l=6, stream_used=7,
+           rows_gathered=8)
 
 
 def round_up(x, m):
@@ -52,19 +53,57 @@ class WalkOutput:
         return {k: int(c[i]) for k, i in CNT.items()}
 
 
+class WalkPlan:
+    """Everything about a pass that does not depend on the embeddings: the walk list of a root batch
+    (walk_ptr), the root-CDF offsets, and the output buffers (reused by every run with this plan)."""
+
+    def __init__(self, sampler, trees, sample_num, for_d, max_path):
+        import torch
+        dev, g = sampler.device, sampler.g
+        R = int(trees.roots.shape[0])
+        self.trees, self.for_d, self.max_path, self.n_roots = trees, bool(for_d), int(max_path), R
+        if isinstance(sample_num, int):
+            self.walk_ptr = torch.arange(R + 1, dtype=torch.int64, device=dev) * sample_num
+            self.n_walks = R * sample_num
+        else:
+            self.walk_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+            self.walk_ptr[1:] = torch.cumsum(sample_num.to(torch.int64), 0)      # plumbing: prefix of sample_num
+            self.n_walks = int(self.walk_ptr[-1].item())
+        r = trees.roots.long()
+        self.rq_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+        self.rq_ptr[1:] = torch.cumsum(g.indptr[r + 1] - g.indptr[r], 0)       # prefix of the roots' walk degrees
+        nq = max(int(self.rq_ptr[-1].item()), 1)
+        self.root_q = torch.empty(nq, dtype=torch.float64, device=dev)
+        self.root_sc = torch.empty(nq, dtype=torch.float32, device=dev)
+        W = max(self.n_walks, 1)
+        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+        self.samples, self.status, self.first_edge, self.wsteps, self.wsuml = i32(W), i32(W), i32(W), i32(W), i32(W)
+        self.paths = i32(W, max_path) if max_path > 0 else None
+        self.path_len = i32(W) if max_path > 0 else None
+        self.root_ok = torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(12, dtype=torch.int64, device=dev)
+        self.row_ptr = torch.empty(R + 1, dtype=torch.int64, device=dev)
+        self.n_rows = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.rows = [i32(max(2 * self.n_walks, 1)) for _ in range(3)] if for_d else None
+
+
 class WalkSampler:
-    def __init__(self, graph):
+    def __init__(self, graph, hub_threshold=256):
         import torch
         self.torch = torch
         self.g = graph
         self.device = graph.device
         self.lib = _cabi.lib()
         self.max_cand = graph.max_deg + 1
+        self.hub_threshold = int(hub_threshold)   # 0 disables both per-pass reuses (pure on-demand path)
         nbytes = C.c_int64(0)
         _cabi.check(self.lib.gg_walk_scratch_bytes(self.max_cand, C.byref(nbytes)), "gg_walk_scratch_bytes")
         self.scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
         self.work_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._bfs_scratch = None
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
 
     # ------------------------------------------------------------------ trees
     def build_trees(self, roots):
@@ -77,70 +116,80 @@ class WalkSampler:
             nbytes = C.c_int64(0)
             _cabi.check(self.lib.gg_bfs_scratch_bytes(N, C.byref(nbytes)), "gg_bfs_scratch_bytes")
             self._bfs_scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
-        st = torch.cuda.current_stream(self.device).cuda_stream
         _cabi.check(self.lib.gg_bfs_build(N, ptr(self.g.indptr), ptr(self.g.adj), R, ptr(roots_d), ptr(parent),
-                                          ptr(self._bfs_scratch), self._bfs_scratch.numel(), st), "gg_bfs_build")
+                                          ptr(self._bfs_scratch), self._bfs_scratch.numel(), self._stream()), "gg_bfs_build")
         return TreeBatch(roots_d, parent)
 
     # ------------------------------------------------------------------ K1
-    def run(self, emb, bias, trees, sample_num, for_d, *, seed=0, pass_tag=0, update_ratio=1.0, max_path=0,
-            rng_mode=RNG_PHILOX, stream=None, finalize=True):
-        """All walks of one pass.  ``sample_num``: int (G mode, config.n_sample_gen) or device
-        int64 [R] (D mode, len(graph[root]))."""
+    def plan(self, trees, sample_num, for_d, max_path=0):
+        return WalkPlan(self, trees, sample_num, for_d, max_path)
+
+    def _desc(self, emb, bias, plan, *, seed, pass_tag, update_ratio, rng_mode, stream, reuse):
         torch = self.torch
-        dev = self.device
-        R = int(trees.roots.shape[0])
-        if isinstance(sample_num, int):
-            walk_ptr = torch.arange(0, (R + 1) * sample_num, max(sample_num, 1), dtype=torch.int64, device=dev)[:R + 1] \
-                if sample_num > 0 else torch.zeros(R + 1, dtype=torch.int64, device=dev)
-            W = R * sample_num
-        else:
-            walk_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
-            walk_ptr[1:] = torch.cumsum(sample_num.to(torch.int64), 0)   # plumbing: prefix of sample_num
-            W = int(walk_ptr[-1].item())
-        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
-        out = WalkOutput(
-            walk_ptr=walk_ptr, n_walks=W, n_roots=R, for_d=bool(for_d), max_path=max_path,
-            samples=i32(max(W, 1)), status=i32(max(W, 1)), first_edge=i32(max(W, 1)), wsteps=i32(max(W, 1)),
-            wsuml=i32(max(W, 1)), paths=i32(max(W, 1), max_path) if max_path > 0 else None,
-            path_len=i32(max(W, 1)) if max_path > 0 else None, root_ok=torch.zeros(max(R, 1), dtype=torch.int32, device=dev),
-            counters=torch.zeros(8, dtype=torch.int64, device=dev), roots=trees.roots)
-        d = _cabi.WalkDesc()
+        assert emb.dtype == torch.float32 and emb.is_contiguous() and bias.dtype == torch.float32
+        t, d = plan.trees, _cabi.WalkDesc()
         d.n_node, d.ld = self.g.n_node, int(emb.shape[1])
         d.emb, d.bias, d.indptr, d.adj = ptr(emb), ptr(bias), ptr(self.g.indptr), ptr(self.g.adj)
-        d.n_roots, d.roots, d.parent, d.walk_ptr, d.n_walks = R, ptr(trees.roots), ptr(trees.parent), ptr(walk_ptr), W
-        d.for_d, d.rng_mode, d.d1_bits = int(bool(for_d)), rng_mode, ptr(self.g.d1_bits)
-        d.seed, d.pass_tag, d.max_path = seed, pass_tag, max_path
+        d.n_roots, d.roots, d.parent, d.walk_ptr, d.n_walks = plan.n_roots, ptr(t.roots), ptr(t.parent), ptr(plan.walk_ptr), plan.n_walks
+        d.for_d, d.rng_mode, d.d1_bits = int(plan.for_d), rng_mode, ptr(self.g.d1_bits)
+        d.seed, d.pass_tag, d.max_path = seed, pass_tag, plan.max_path
         d.stream, d.n_stream = (ptr(stream), int(stream.numel())) if stream is not None else (None, 0)
         d.update_ratio, d.max_cand = float(update_ratio), self.max_cand
-        d.samples, d.status, d.first_edge, d.wsteps, d.wsuml = (ptr(out.samples), ptr(out.status), ptr(out.first_edge),
-                                                                 ptr(out.wsteps), ptr(out.wsuml))
-        d.paths, d.path_len, d.counters = ptr(out.paths), ptr(out.path_len), ptr(out.counters)
+        d.samples, d.status, d.first_edge, d.wsteps, d.wsuml = (ptr(plan.samples), ptr(plan.status), ptr(plan.first_edge),
+                                                                 ptr(plan.wsteps), ptr(plan.wsuml))
+        d.paths, d.path_len, d.counters = ptr(plan.paths), ptr(plan.path_len), ptr(plan.counters)
         d.scratch, d.scratch_bytes, d.work_counter = ptr(self.scratch), self.scratch.numel(), ptr(self.work_counter)
-        assert emb.dtype == torch.float32 and emb.is_contiguous() and bias.dtype == torch.float32
-        st = torch.cuda.current_stream(dev).cuda_stream
-        _cabi.check(self.lib.gg_walk_sample(C.byref(d), st), "gg_walk_sample")
+        d.rq_ptr = ptr(plan.rq_ptr)
+        if reuse:
+            self.g.hub_tiles(self.hub_threshold)
+            d.edge_score, d.hub_threshold, d.root_q = ptr(self.g.edge_score), self.hub_threshold, ptr(plan.root_q)
+        return d
+
+    def precompute(self, emb, bias, plan, desc=None):
+        """Per-pass reuse (csrc/hub.cu): hub adjacency scores, then one CDF per root.  Depends on the
+        embeddings, so it belongs to every pass; `run` calls it unless told otherwise."""
+        d = desc if desc is not None else self._desc(emb, bias, plan, seed=0, pass_tag=0, update_ratio=1.0,
+                                                     rng_mode=RNG_PHILOX, stream=None, reuse=True)
+        tile_node, tile_begin, n_tiles, _ = self.g.hub_tiles(self.hub_threshold)
+        st = self._stream()
+        _cabi.check(self.lib.gg_hub_scores(n_tiles, ptr(tile_node), ptr(tile_begin), 256, ptr(self.g.indptr), ptr(self.g.adj),
+                                           ptr(emb), ptr(bias), int(emb.shape[1]), ptr(self.g.edge_score), st), "gg_hub_scores")
+        _cabi.check(self.lib.gg_root_cdf(C.byref(d), ptr(plan.root_sc), ptr(plan.root_q), st), "gg_root_cdf")
+
+    def run(self, emb, bias, trees, sample_num, for_d, *, seed=0, pass_tag=0, update_ratio=1.0, max_path=0,
+            rng_mode=RNG_PHILOX, stream=None, finalize=True, plan=None, reuse=None, precompute=True):
+        """All walks of one pass.  ``sample_num``: int (G mode, config.n_sample_gen) or device int64 [R]
+        (D mode, len(graph[root])).  ``reuse`` (default: hub_threshold > 0) turns the per-pass score / CDF
+        reuse on; results are bit-identical either way."""
+        if plan is None:
+            plan = self.plan(trees, sample_num, for_d, max_path)
+        reuse = (self.hub_threshold > 0) if reuse is None else bool(reuse)
+        plan.counters.zero_()
+        d = self._desc(emb, bias, plan, seed=seed, pass_tag=pass_tag, update_ratio=update_ratio, rng_mode=rng_mode,
+                       stream=stream, reuse=reuse)
+        if reuse and precompute:
+            self.precompute(emb, bias, plan, d)
+        _cabi.check(self.lib.gg_walk_sample(C.byref(d), self._stream()), "gg_walk_sample")
+        out = WalkOutput(walk_ptr=plan.walk_ptr, n_walks=plan.n_walks, n_roots=plan.n_roots, for_d=plan.for_d,
+                         max_path=plan.max_path, samples=plan.samples, status=plan.status, first_edge=plan.first_edge,
+                         wsteps=plan.wsteps, wsuml=plan.wsuml, paths=plan.paths, path_len=plan.path_len,
+                         root_ok=plan.root_ok, counters=plan.counters, roots=trees.roots, plan=plan)
         if finalize:
             self.finalize(out)
         return out
 
     def finalize(self, out):
-        st = self.torch.cuda.current_stream(self.device).cuda_stream
         _cabi.check(self.lib.gg_walk_finalize(out.n_roots, ptr(out.walk_ptr), int(out.for_d), ptr(out.samples),
                                               ptr(out.status), ptr(out.first_edge), ptr(out.wsteps), ptr(out.wsuml),
                                               ptr(out.path_len), ptr(self.g.d1_bits), ptr(out.root_ok),
-                                              ptr(out.counters), st), "gg_walk_finalize")
+                                              ptr(out.counters), self._stream()), "gg_walk_finalize")
 
     def emit_d_rows(self, out):
         """prepare_data_for_d's (center, neighbor, label) rows (graph_gan.py:192-201), on device."""
-        torch = self.torch
-        dev = self.device
-        cap = 2 * out.n_walks
-        row_ptr = torch.empty(out.n_roots + 1, dtype=torch.int64, device=dev)
-        n_rows = torch.zeros(1, dtype=torch.int64, device=dev)
-        center, neighbor, label = (torch.empty(max(cap, 1), dtype=torch.int32, device=dev) for _ in range(3))
-        st = torch.cuda.current_stream(dev).cuda_stream
+        p = out.plan
+        center, neighbor, label = p.rows
         _cabi.check(self.lib.gg_emit_d_rows(out.n_roots, ptr(out.roots), ptr(out.walk_ptr), ptr(self.g.raw_indptr),
-                                            ptr(self.g.raw_adj), ptr(out.root_ok), ptr(out.samples), ptr(row_ptr),
-                                            ptr(center), ptr(neighbor), ptr(label), ptr(n_rows), st), "gg_emit_d_rows")
-        return center, neighbor, label, n_rows
+                                            ptr(self.g.raw_adj), ptr(out.root_ok), ptr(out.samples), ptr(p.row_ptr),
+                                            ptr(center), ptr(neighbor), ptr(label), ptr(p.n_rows), self._stream()),
+                    "gg_emit_d_rows")
+        return center, neighbor, label, p.n_rows

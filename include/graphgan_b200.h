@@ -42,7 +42,8 @@ enum {
 enum {
     GG_CNT_STEPS = 0, GG_CNT_SUML = 1, GG_CNT_ACCEPTED = 2, GG_CNT_OK_ROOTS = 3,
     GG_CNT_PATH_OVERFLOW = 4, GG_CNT_RAW_STEPS = 5, GG_CNT_RAW_SUML = 6, GG_CNT_STREAM_USED = 7,
-    GG_CNT_SLOTS = 8
+    GG_CNT_ROWS_GATHERED = 8, /* embedding rows the walk kernel actually fetched (on-demand scores + cur rows) */
+    GG_CNT_SLOTS = 12
 };
 
 const char *gg_last_error(void);
@@ -91,7 +92,26 @@ typedef struct gg_walk_desc {
     void *scratch;              /* device, gg_walk_scratch_bytes(max_cand) */
     int64_t scratch_bytes;
     unsigned int *work_counter; /* device, 1 word, zeroed by the call */
+    /* optional per-pass precomputation (identical results, far less traffic) */
+    const float *edge_score;    /* device [nnz] all_score[u, adj[e]] for walk-CSR entries of nodes with
+                                   degree >= hub_threshold (gg_hub_scores); NULL = always score on demand */
+    const double *root_q;       /* device: per root, the normalised CDF of its root step (gg_root_cdf);
+                                   NULL = compute the root step per walk */
+    const int64_t *rq_ptr;      /* device [R+1] offsets into root_q (prefix of the roots' walk-CSR degrees) */
+    int32_t hub_threshold;
+    int32_t reserved2;
 } gg_walk_desc;
+
+/* all_score[u, v] = e_u.e_v + b_v (generator.py:21) for every walk-CSR entry (u -> v) of the listed hub
+ * tiles: tile t covers entries [tile_begin[t], min(tile_begin[t] + tile_edges, indptr[tile_node[t]+1])).
+ * Must be re-run whenever the generator's embeddings change (i.e. once per sampling pass). */
+int gg_hub_scores(int64_t n_tiles, const int32_t *tile_node, const int64_t *tile_begin, int32_t tile_edges,
+                  const int64_t *indptr, const int32_t *adj, const float *emb, const float *bias, int32_t ld,
+                  float *edge_score, void *stream);
+/* Root-step softmax + CDF, once per root per pass: root_q[rq_ptr[k] + i] = cdf_i / cdf_last over the
+ * candidates tree[root][1:] (graph_gan.py:250,260-262).  Uses d->{roots, n_roots, indptr, adj, emb, bias,
+ * ld, rq_ptr, edge_score, hub_threshold}.  root_sc: device float scratch of rq_ptr[R] entries. */
+int gg_root_cdf(const gg_walk_desc *d, float *root_sc, double *root_q, void *stream);
 
 int gg_walk_scratch_bytes(int32_t max_cand, int64_t *bytes);
 int gg_walk_sample(const gg_walk_desc *d, void *stream);
@@ -138,12 +158,22 @@ int gg_all_score(int64_t n_node, const float *emb, const float *bias, int32_t ld
  *   mode 0 = discriminator loss (discriminator.py:26-30), aux = label
  *   mode 1 = generator loss     (generator.py:26-29),     aux = reward
  * outputs: n_unique (device int32), uniq_ids[2B], grad_rows[2B, ld], grad_bias[2B],
- * row_slot: device [N] int32 map, must be all -1 on entry; set for touched rows. */
+ * row_slot: device [N] int32 map, must be all -1 on entry; set for touched rows.
+ * batch_total: size of the whole mini-batch when n_pairs is one rank's slice of it (the generator
+ * loss is a MEAN over the batch, generator.py:28); 0 = n_pairs. */
 #define GG_MAX_BATCH 1024
-int gg_pair_grad(int32_t mode, int32_t n_pairs, const int32_t *node_id,
+int gg_pair_grad(int32_t mode, int32_t n_pairs, int32_t batch_total, const int32_t *node_id,
                  const int32_t *node_neighbor_id, const float *aux, const float *emb,
                  const float *bias, int32_t ld, float lambda, int32_t *n_unique, int32_t *uniq_ids,
                  float *grad_rows, float *grad_bias, int32_t *row_slot, void *stream);
+
+/* Data-parallel step: merge the compact gradients of `world` ranks (each laid out as one buffer of
+ * gg_grad_buf_floats(cap, ld) floats: rows[cap, ld] | bias[cap] | ids[cap] (int32 bits) | n_unique) into
+ * the final unique/summed form, rank-major entry order -- every rank computes the identical result
+ * from the all-gathered buffers, so replicas stay bit-identical.  Clears and re-sets row_slot. */
+int64_t gg_grad_buf_floats(int32_t cap, int32_t ld);
+int gg_grad_merge(int32_t world, int32_t cap, int32_t ld, const float *gathered, int32_t *n_unique,
+                  int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot, void *stream);
 
 /* K3: TF1.8 AdamOptimizer sparse apply == dense decay (generator.py:30-31,
  * discriminator.py:31-32): m <- b1*m (+ (1-b1) g on touched rows), v likewise, then for ALL

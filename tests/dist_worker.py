@@ -1,0 +1,103 @@
+"""Worker for the multi-process tests (launched by tests/test_dist.py through torch.distributed.run).
+
+  mode "cpu": gloo, host logic only (no kernels): partitioning + variable-length all-gather.
+  mode "gpu": nccl, one rank per GPU: root-sharded sampling is invariant, data-parallel updates match the
+              single-GPU step and keep the replicas bit-identical.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(mode):
+    import torch
+    import torch.distributed as dist
+    from graphgan_b200 import parallel
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if mode == "cpu":
+        dist.init_process_group("gloo")
+        # block ranges tile [0, n) in rank order
+        for n in (0, 1, 7, 64, 65):
+            rngs = [parallel.block_range(n, r, world) for r in range(world)]
+            assert rngs[0][0] == 0 and rngs[-1][1] == n and all(rngs[k][1] == rngs[k + 1][0] for k in range(world - 1))
+            assert max(b - a for a, b in rngs) - min(b - a for a, b in rngs) <= 1
+        w = np.random.RandomState(0).pareto(1.5, size=1000) + 1
+        rr = parallel.balanced_root_ranges(w, world)
+        assert rr[0][0] == 0 and rr[-1][1] == 1000 and all(rr[k][1] == rr[k + 1][0] for k in range(world - 1))
+        tot = [w[a:b].sum() for a, b in rr]
+        assert max(tot) <= w.sum() / world + w.max() + 1e-9
+        # variable-length gather keeps rank order
+        mine = torch.arange(rank * 100, rank * 100 + 3 + 2 * rank, dtype=torch.int32)
+        got = parallel.all_gather_varlen(mine)
+        want = torch.cat([torch.arange(r * 100, r * 100 + 3 + 2 * r, dtype=torch.int32) for r in range(world)])
+        assert torch.equal(got, want)
+        empty = parallel.all_gather_varlen(torch.zeros(0 if rank else 2, dtype=torch.float32))
+        assert empty.shape[0] == 2
+        dist.barrier()
+        if rank == 0:
+            print("DIST_CPU_OK")
+        dist.destroy_process_group()
+        return
+    # ------------------------------------------------------------------ gpu
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from graphgan_b200 import graph as G, sampler as S, synth
+    from graphgan_b200.discriminator import Discriminator
+    from graphgan_b200.generator import Generator
+    n, d = 4000, 128
+    hg = G.HostGraph(synth.power_law(n, 12, seed=2), None, n_node=n)
+    dg = G.DeviceGraph(hg, dev)
+    smp = S.WalkSampler(dg)
+    emb = S.pad_embedding(synth.embeddings(n, d, seed=3), dev)
+    bias = torch.zeros(n, dtype=torch.float32, device=dev)
+    roots = synth.pick_roots(hg.degrees(), 600, seed=4)
+    # (1) root-sharded sampling == single-GPU sampling (Philox is keyed by root, walk, step)
+    lo, hi = parallel.balanced_root_ranges(hg.degrees()[roots], world)[rank]
+    mine = roots[lo:hi]
+    t = smp.build_trees(mine)
+    out = smp.run(emb, bias, t, dg.raw_deg[t.roots.long()], True, seed=11, pass_tag=1)
+    c, nb, lb, k = smp.emit_d_rows(out)
+    k = int(k.item())
+    gc, gn, gl = (parallel.all_gather_varlen(x[:k]) for x in (c, nb, lb))
+    if rank == 0:
+        dg.reset_tree_mutations()
+        tf = smp.build_trees(roots)
+        of = smp.run(emb, bias, tf, dg.raw_deg[tf.roots.long()], True, seed=11, pass_tag=1)
+        fc, fn, fl, fk = smp.emit_d_rows(of)
+        fk = int(fk.item())
+        assert fk == gc.shape[0] and torch.equal(fc[:fk], gc) and torch.equal(fn[:fk], gn) and torch.equal(fl[:fk], gl)
+    # (2) data-parallel updates
+    rs = np.random.RandomState(5)
+    e0 = rs.normal(0, 0.5, size=(n, d))
+    for cls, mode in ((Discriminator, 0), (Generator, 1)):
+        single, repl = cls(n, e0, device=dev), cls(n, e0, device=dev)
+        dp = parallel.DataParallelStep(repl)
+        for step in range(5):
+            B = (64, 64, 63, 5, 1)[step]
+            i, j = rs.randint(0, n, B).astype(np.int32), rs.randint(0, n, B).astype(np.int32)
+            if B > 4:
+                i[1], j[1] = i[0], j[0]
+            aux = ((rs.random_sample(B) < 0.5) if mode == 0 else rs.random_sample(B) * 3).astype(np.float32)
+            single.step(i, j, aux)
+            dp.step(i, j, aux)
+            a, b = single.emb.double(), repl.emb.double()
+            assert float((a - b).norm() / a.norm()) <= 1e-5, (cls.__name__, step)
+            assert int((repl.row_slot != -1).sum()) == 0
+        # replicas bit-identical across ranks
+        rows = [torch.empty_like(repl.emb) for _ in range(world)]
+        dist.all_gather(rows, repl.emb)
+        assert all(torch.equal(rows[0], r) for r in rows[1:])
+    dist.barrier()
+    if rank == 0:
+        print("DIST_GPU_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -38,7 +38,7 @@ def test_cabi_argument_errors_do_not_abort():
     assert lib.gg_walk_scratch_bytes(0, C.byref(n)) != 0       # bad max_cand -> error code + message
     assert b"gg_walk_scratch_bytes" in lib.gg_last_error()
     assert lib.gg_walk_sample(None, None) != 0
-    assert lib.gg_pair_grad(7, 1, None, None, None, None, None, 32, C.c_float(0), None, None, None, None, None, None) != 0
+    assert lib.gg_pair_grad(7, 1, 0, None, None, None, None, None, 32, C.c_float(0), None, None, None, None, None, None) != 0
     with pytest.raises(_cabi.GGError):
         _cabi.check(lib.gg_bfs_build(10, None, None, 1, None, None, None, 0, None), "gg_bfs_build")
 

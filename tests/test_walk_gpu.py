@@ -11,7 +11,7 @@ from tests.golden import loader
 pytestmark = pytest.mark.gpu
 
 
-def _setup(case, cuda_device, roots=None):
+def _setup(case, cuda_device, roots=None, hub_threshold=256):
     import torch
     from graphgan_b200 import graph as G, sampler as S
     from oracle import canonical as can
@@ -24,7 +24,7 @@ def _setup(case, cuda_device, roots=None):
     indptr, adj = can.unique_csr(case.graph)
     assert np.array_equal(hg.indptr, indptr) and np.array_equal(hg.adj, adj)
     dg = G.DeviceGraph(hg, cuda_device)
-    smp = S.WalkSampler(dg)
+    smp = S.WalkSampler(dg, hub_threshold=hub_threshold)
     roots = np.arange(case.n, dtype=np.int32) if roots is None else np.asarray(roots, np.int32)
     trees = smp.build_trees(roots)
     emb = S.pad_embedding(case.emb_g, cuda_device)
@@ -58,14 +58,15 @@ def test_bfs_matches_reference_order(name, cuda_device):
         assert np.array_equal(got, case["parent"][roots])
 
 
+@pytest.mark.parametrize("hub", [0, 8])
 @pytest.mark.parametrize("name", ["tiny", "rand300", "rand1200", "cagrqc"])
-def test_stream_replay_matches_reference(name, cuda_device):
+def test_stream_replay_matches_reference(name, hub, cuda_device):
     """Feed the MT19937 doubles the reference consumed; the GPU must reproduce the reference's
     prepare_data_for_d rows, its tree mutations, and then (G pass on the mutated trees) its paths."""
     import torch
     from graphgan_b200 import sampler as S
     case = loader.load(name)
-    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device)
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, hub_threshold=hub)
     st = torch.as_tensor(loader.stream(case)).to(cuda_device)
     out = smp.run(emb, bias, trees, dg.raw_deg, True, rng_mode=S.RNG_STREAM, stream=st)
     c, nb, lb, n_rows = smp.emit_d_rows(out)
@@ -94,11 +95,11 @@ def test_stream_replay_matches_reference(name, cuda_device):
         assert got[k] == pf[pp[k]:pp[k + 1]].tolist()
 
 
-def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen):
+def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256):
     import torch
     from graphgan_b200 import sampler as S
     from oracle import canonical as can
-    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots)
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold)
     par = trees.parent.cpu().numpy()
     E = can.pad_rows(case.emb_g)
     bits = np.zeros(dg.n_bit_words, np.uint32)
@@ -137,13 +138,18 @@ def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen):
     return cnt, cg
 
 
+@pytest.mark.parametrize("hub", [0, 8, 256])
 @pytest.mark.parametrize("name,ratio", [("tiny", 1.0), ("rand300", 1.0), ("rand300", 0.6), ("rand1200", 1.0), ("cagrqc", 1.0)])
-def test_philox_matches_canonical_oracle(name, ratio, cuda_device):
+def test_philox_matches_canonical_oracle(name, ratio, hub, cuda_device):
+    """hub = 0: every score on demand, root step per walk; hub = 8 / 256: per-pass hub scores and root
+    CDFs (csrc/hub.cu).  Identical bits either way."""
     case = loader.load(name)
-    _philox_compare(case, cuda_device, None, ratio, seed=0x1234567 + 17, n_sample_gen=int(case.n_sample_gen))
+    _philox_compare(case, cuda_device, None, ratio, seed=0x1234567 + 17, n_sample_gen=int(case.n_sample_gen),
+                    hub_threshold=hub)
 
 
-def test_hub_lists_use_global_scratch(cuda_device):
+@pytest.mark.parametrize("hub", [0, 64, 256])
+def test_hub_lists_use_global_scratch(hub, cuda_device):
     """A power-law graph whose hub has > SMEM_CAP neighbours: the long-list (global scratch) path
     and multi-tile softmax must agree bit-for-bit with the oracle as well."""
     from graphgan_b200 import synth
@@ -157,5 +163,7 @@ def test_hub_lists_use_global_scratch(cuda_device):
     case["graph"] = [hg.neighbors(i).tolist() for i in range(n)]
     rs = np.random.RandomState(0)
     roots = np.sort(rs.choice(np.flatnonzero(hg.degrees() > 0), 400, replace=False))
-    cnt, cg = _philox_compare(case, cuda_device, roots, 1.0, seed=99, n_sample_gen=6)
+    cnt, cg = _philox_compare(case, cuda_device, roots, 1.0, seed=99, n_sample_gen=6, hub_threshold=hub)
     assert cnt["steps"] > 0
+    if hub:   # the reuse must actually remove row gathers
+        assert cnt["rows_gathered"] < cnt["raw_sum_l"]
