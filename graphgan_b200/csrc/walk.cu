@@ -69,24 +69,35 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             inc_father = step > 0;
             if (d.for_d && step == 1) inc_father = false;
             if (!d.for_d && step == 1 && ((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u)) inc_father = false;
-            const bool in_smem = (a1 - a0 + 1) <= SMEM_CAP;
             const bool cached = d.edge_score && (a1 - a0) >= d.hub_threshold;  // scores precomputed per pass
-            int *ids = in_smem ? s_ids : g_ids;
-            float *sc = in_smem ? s_sc : g_sc;
+            int *ids = (a1 - a0 + 1) <= ID_CAP ? s_ids : g_ids;
+            float *sc = (a1 - a0 + 1) <= SC_CAP ? s_sc : g_sc;
             n = 0;
             if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
-            for (long long e0 = a0; e0 < a1; e0 += 32) {
-                const long long e = e0 + lane;
-                int v = -1;
-                if (e < a1) v = __ldg(d.adj + e);
-                const bool isc = (v >= 0) && (__ldg(par + v) == cur);
-                const unsigned mk = __ballot_sync(FULL, isc);
-                if (isc) {
-                    const int pos = n + __popc(mk & ((1u << lane) - 1u));
-                    ids[pos] = v;
-                    if (cached) sc[pos] = __ldg(d.edge_score + e);
+            float m = -INFINITY;   // running max of the cached scores (lane local)
+            const unsigned lt = (1u << lane) - 1u;
+            for (long long e0 = a0; e0 < a1; e0 += 32 * UNR) {   // UNR adjacency tiles in flight
+                int v[UNR], p[UNR];
+                float cs[UNR];
+#pragma unroll
+                for (int k = 0; k < UNR; ++k) {
+                    const long long e = e0 + 32 * k + lane;
+                    v[k] = (e < a1) ? __ldg(d.adj + e) : -1;
+                    cs[k] = (cached && e < a1) ? __ldg(d.edge_score + e) : 0.0f;
                 }
-                n += __popc(mk);
+#pragma unroll
+                for (int k = 0; k < UNR; ++k) p[k] = (v[k] >= 0) ? __ldg(par + v[k]) : -2;
+#pragma unroll
+                for (int k = 0; k < UNR; ++k) {
+                    const bool isc = p[k] == cur;
+                    const unsigned mk = __ballot_sync(FULL, isc);
+                    if (isc) {
+                        const int pos = n + __popc(mk & lt);
+                        ids[pos] = v[k];
+                        if (cached) { sc[pos] = cs[k]; m = fmaxf(m, cs[k]); }
+                    }
+                    n += __popc(mk);
+                }
             }
             __syncwarp();
             if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
@@ -98,11 +109,17 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
                 score_list<CPL>(d.emb, d.bias, ld, c4, ids, sc, cached ? 1 : n, cur, lane);
                 rows_gathered += 1u + (unsigned)(cached ? 1 : n);
             }
+            if (cached) {
+                m = warp_max(m);
+                if (inc_father) m = fmaxf(m, sc[0]);
+            } else {
+                m = list_max(sc, n, lane);
+            }
 
             // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
             const double u = rng.draw((uint32_t)root, k, (uint32_t)step);
             if (rng.exhausted) { status = GG_NOTRUN; break; }
-            idx = choose_index(sc, n, u, lane);
+            idx = choose_index(sc, n, m, u, lane);
             nxt = ids[idx];
             __syncwarp();
         }
@@ -128,10 +145,11 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
 
 // ---------------------------------------------------------------- order-free (Philox) kernel
 template <int CPL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_kernel(const __grid_constant__ gg_walk_desc d) {
-    __shared__ int s_ids[WARPS_PER_CTA][SMEM_CAP];
-    __shared__ float s_sc[WARPS_PER_CTA][SMEM_CAP];
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_kernel(const __grid_constant__ gg_walk_desc d) {
+    extern __shared__ __align__(16) unsigned char walk_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
+    int *s_ids = reinterpret_cast<int *>(s_sc + SC_CAP);
     const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
     int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
     float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
@@ -166,8 +184,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_kernel(const __grid_c
                 continue;
             }
         }
-        walk_one<CPL>(d, rng, slot, k, w, s_ids[wid], s_sc[wid], g_ids, g_sc, lane, raw_steps, raw_suml, overflow,
-                      rows_gathered);
+        walk_one<CPL>(d, rng, slot, k, w, s_ids, s_sc, g_ids, g_sc, lane, raw_steps, raw_suml, overflow, rows_gathered);
     }
     if (lane == 0) {
         if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
@@ -182,8 +199,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_kernel(const __grid_c
 // root (graph_gan.py:189/209), a draw per choice (:262), stop at a root's first void.
 template <int CPL>
 __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__ gg_walk_desc d) {
-    __shared__ int s_ids[SMEM_CAP];
-    __shared__ float s_sc[SMEM_CAP];
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    float *s_sc = reinterpret_cast<float *>(walk_smem);
+    int *s_ids = reinterpret_cast<int *>(s_sc + SC_CAP);
     const int lane = threadIdx.x;
     int *g_ids = reinterpret_cast<int *>(d.scratch);
     float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
@@ -288,7 +306,7 @@ __global__ void emit_rows_kernel(long long n_roots, const int *roots, const long
     }
 }
 
-int grid_ctas() { return sm_count() * 4; }
+int grid_ctas() { return sm_count() * 3; }
 
 }  // namespace
 }  // namespace gg
@@ -320,20 +338,30 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
         GG_REQUIRE(d.stream, "stream mode needs the uniform stream");
         GG_REQUIRE(d.scratch_bytes >= 2ll * d.max_cand * 4, "scratch too small");
         switch (cpl) {
-            case 1: gg::walk_stream_kernel<1><<<1, 32, 0, st>>>(d); break;
-            case 2: gg::walk_stream_kernel<2><<<1, 32, 0, st>>>(d); break;
-            case 4: gg::walk_stream_kernel<4><<<1, 32, 0, st>>>(d); break;
-            case 8: gg::walk_stream_kernel<8><<<1, 32, 0, st>>>(d); break;
+#define GG_STREAM(C)                                                                                                  \
+    GG_CHECK(cudaFuncSetAttribute(gg::walk_stream_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                  gg::WALK_SMEM_PER_WARP));                                                          \
+    gg::walk_stream_kernel<C><<<1, 32, gg::WALK_SMEM_PER_WARP, st>>>(d)
+            case 1: GG_STREAM(1); break;
+            case 2: GG_STREAM(2); break;
+            case 4: GG_STREAM(4); break;
+            case 8: GG_STREAM(8); break;
+#undef GG_STREAM
             default: gg::set_error("gg_walk_sample: unsupported ld %d (supported: 32, 64, 128, 256)", d.ld); return 2;
         }
     } else {
         const int ctas = gg::grid_ctas();
         GG_REQUIRE(d.scratch_bytes >= (int64_t)ctas * gg::WARPS_PER_CTA * 2 * d.max_cand * 4, "scratch too small");
         switch (cpl) {
-            case 1: gg::walk_kernel<1><<<ctas, gg::WARPS_PER_CTA * 32, 0, st>>>(d); break;
-            case 2: gg::walk_kernel<2><<<ctas, gg::WARPS_PER_CTA * 32, 0, st>>>(d); break;
-            case 4: gg::walk_kernel<4><<<ctas, gg::WARPS_PER_CTA * 32, 0, st>>>(d); break;
-            case 8: gg::walk_kernel<8><<<ctas, gg::WARPS_PER_CTA * 32, 0, st>>>(d); break;
+#define GG_WALK(C)                                                                                                    \
+    GG_CHECK(cudaFuncSetAttribute(gg::walk_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
+                                  gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                      \
+    gg::walk_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d)
+            case 1: GG_WALK(1); break;
+            case 2: GG_WALK(2); break;
+            case 4: GG_WALK(4); break;
+            case 8: GG_WALK(8); break;
+#undef GG_WALK
             default: gg::set_error("gg_walk_sample: unsupported ld %d (supported: 32, 64, 128, 256)", d.ld); return 2;
         }
     }

@@ -7,7 +7,11 @@
 namespace gg {
 
 constexpr int WARPS_PER_CTA = 8;
-constexpr int SMEM_CAP = 320;  // candidates per warp kept in shared memory (ids + scores)
+constexpr int ID_CAP = 320;    // candidate ids per warp kept in shared memory (longer lists: global scratch)
+constexpr int SC_CAP = 2048;   // candidate scores per warp kept in shared memory
+constexpr int SMEM_CAP = ID_CAP;
+constexpr int WALK_SMEM_PER_WARP = SC_CAP * 4 + ID_CAP * 4;
+constexpr int UNR = 4;         // tiles of 32 candidates in flight per pass iteration
 
 // cur row in registers: lane (grp, g) holds float4 chunks g, g+8, ... (replicated over the 4 groups)
 template <int CPL>
@@ -84,18 +88,29 @@ __device__ __forceinline__ void score_edges(const float *__restrict__ emb, const
     __syncwarp();
 }
 
-// softmax numerators in place (sc[i] <- e_i) and their canonical sum S.
-__device__ __forceinline__ float softmax_exp_sum(float *sc, int n, int lane) {
+// max over sc[0..n)
+__device__ __forceinline__ float list_max(const float *sc, int n, int lane) {
     float m = -INFINITY;
     for (int i = lane; i < n; i += 32) m = fmaxf(m, sc[i]);
-    m = warp_max(m);
+    return warp_max(m);
+}
+
+// softmax numerators in place (sc[i] <- e_i = exp_c(s_i - m)) and their canonical sum
+// S = T_0 + T_1 + ... (tile sums by butterfly; 0 + T_0 == T_0 and S + 0 == S exactly, so empty
+// tiles of the unrolled tail are harmless).  UNR tiles are in flight per iteration.
+__device__ __forceinline__ float softmax_exp_sum(float *sc, int n, float m, int lane) {
     float S = 0.0f;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-        const int i = t0 + lane;
-        float e = 0.0f;
-        if (i < n) { e = exp_c(__fsub_rn(sc[i], m)); sc[i] = e; }
-        const float T = warp_sum_butterfly(e);
-        S = (t0 == 0) ? T : __fadd_rn(S, T);
+    for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
+        float x[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; x[u] = (i < n) ? sc[i] : 0.0f; }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = t0 + 32 * u + lane;
+            float e = 0.0f;
+            if (i < n) { e = exp_c(__fsub_rn(x[u], m)); sc[i] = e; }
+            S = __fadd_rn(S, warp_sum_butterfly(e));
+        }
     }
     __syncwarp();
     return S;
@@ -104,35 +119,52 @@ __device__ __forceinline__ float softmax_exp_sum(float *sc, int n, int lane) {
 // total of the float64 CDF over p_i = e_i / S
 __device__ __forceinline__ double cdf_total(const float *sc, int n, float S, int lane) {
     double total = 0.0;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-        const int i = t0 + lane;
-        double x = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;
-        x = warp_scan_ks(x, lane);
-        total = __dadd_rn(total, __shfl_sync(FULL, x, 31));
+    for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
+        float e[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? sc[i] : 0.0f; }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            double x = (double)__fdiv_rn(e[u], S);   // 0 / S == 0 for the padding lanes
+            x = warp_scan_ks(x, lane);
+            total = __dadd_rn(total, __shfl_sync(FULL, x, 31));
+        }
     }
     return total;
 }
 
-// softmax + CDF + draw over sc[0..n) (== ggo_choose).  All lanes return the index.
-__device__ __forceinline__ int choose_index(float *sc, int n, double u, int lane) {
-    const float S = softmax_exp_sum(sc, n, lane);
-    const double total = cdf_total(sc, n, S, lane);
+// first i with cdf_i / total > u; all lanes return it
+__device__ __forceinline__ int cdf_pick(const float *sc, int n, float S, double total, double u, int lane) {
     double carry = 0.0;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-        const int i = t0 + lane;
-        double x = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;
-        x = warp_scan_ks(x, lane);
-        const double q = __ddiv_rn(__dadd_rn(carry, x), total);
-        const unsigned hit = __ballot_sync(FULL, (i < n) && (q > u));
-        if (hit) return t0 + __ffs(hit) - 1;
-        carry = __dadd_rn(carry, __shfl_sync(FULL, x, 31));
+    for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
+        float e[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) { const int i = t0 + 32 * k + lane; e[k] = (i < n) ? sc[i] : 0.0f; }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const int i = t0 + 32 * k + lane;
+            double x = (double)__fdiv_rn(e[k], S);
+            x = warp_scan_ks(x, lane);
+            const double q = __ddiv_rn(__dadd_rn(carry, x), total);
+            const unsigned hit = __ballot_sync(FULL, (i < n) && (q > u));
+            if (hit) return t0 + 32 * k + __ffs(hit) - 1;
+            carry = __dadd_rn(carry, __shfl_sync(FULL, x, 31));
+        }
     }
     return n - 1;
 }
 
+// softmax + CDF + draw over sc[0..n) given its max m (== ggo_choose).  All lanes return the index.
+__device__ __forceinline__ int choose_index(float *sc, int n, float m, double u, int lane) {
+    const float S = softmax_exp_sum(sc, n, m, lane);
+    const double total = cdf_total(sc, n, S, lane);
+    return cdf_pick(sc, n, S, total, u, lane);
+}
+
 // normalised CDF q_i = cdf_i / total written out (the array numpy's choice would searchsorted)
 __device__ __forceinline__ void cdf_store(float *sc, int n, double *q_out, int lane) {
-    const float S = softmax_exp_sum(sc, n, lane);
+    const float m = list_max(sc, n, lane);
+    const float S = softmax_exp_sum(sc, n, m, lane);
     const double total = cdf_total(sc, n, S, lane);
     double carry = 0.0;
     for (int t0 = 0; t0 < n; t0 += 32) {

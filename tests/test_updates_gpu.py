@@ -50,7 +50,9 @@ def test_discriminator_steps_match_oracle(n, d, B, cuda_device):
     ora = updates.Discriminator(n, emb, 1e-3, 1e-5)
     for (i, j) in _batches(rs, n, 6, B):
         lab = (rs.random_sample(B) < 0.5).astype(np.float32)
-        assert np.allclose(dev_m.reward_pairs(i, j).cpu().numpy(), ora.reward(i, j), rtol=RTOL, atol=1e-6)
+        # reward = softplus(score): its absolute error is the score's (<= |s| * 2^-23 * O(log d) ~ 5e-6 at |s| ~ 10,
+        # the summation orders differ), so the bar is 1e-5 relative + that absolute floor
+        assert np.allclose(dev_m.reward_pairs(i, j).cpu().numpy(), ora.reward(i, j), rtol=RTOL, atol=5e-6)
         dev_m.d_step(i, j, lab)
         ora.d_updates(i, j, lab)
         assert close(dev_m.embedding_numpy(), ora.E) and close(dev_m.bias_t.cpu().numpy(), ora.b)

@@ -3,8 +3,9 @@ import numpy as np, torch
 from graphgan_b200.discriminator import Discriminator
 from oracle import updates
 dev = torch.device('cuda:0')
-for (n, d, B) in [(500, 50, 64), (300, 128, 33)]:
+for (n, d, B) in [(400, 256, 128)]:
     rs = np.random.RandomState(n + d)
+    print('CONFIG', n, d, B)
     emb = rs.normal(0, 0.5, size=(n, d))
     dm = Discriminator(n, emb, device=dev); ora = updates.Discriminator(n, emb, 1e-3, 1e-5)
     for step in range(6):
@@ -22,4 +23,5 @@ for (n, d, B) in [(500, 50, 64), (300, 128, 33)]:
         dm.apply_adam(); ora.adam.apply(ora.E, ora.b, rows, g_rows, g_bias)
         E = dm.embedding_numpy(); dif = np.abs(E - ora.E); rel = dif / (np.abs(ora.E) + 1e-30)
         k = np.unravel_index(np.argmax(dif), dif.shape)
+        print('   fro', np.linalg.norm(E.astype(np.float64)-ora.E)/np.linalg.norm(ora.E), 'okfrac', float(np.mean(dif <= 1e-5*np.abs(ora.E)+1e-6)), 'n>1e-5', int((dif>1e-5).sum()), 'n>1e-4', int((dif>1e-4).sum()))
         print('   emb maxabs', dif.max(), 'at', k, E[k], ora.E[k], 'viol', int((dif > 1e-5 * np.abs(ora.E) + 2e-7).sum()), 'm diff', np.abs(dm.m_emb[:, :d].cpu().numpy() - ora.adam.m_e).max(), 'v rel', (np.abs(dm.v_emb[:, :d].cpu().numpy() - ora.adam.v_e) / (ora.adam.v_e + 1e-30)).max())
