@@ -37,7 +37,7 @@ WORKLOADS = {
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="powerlaw_1m", choices=sorted(WORKLOADS))
@@ -45,6 +45,7 @@ def parse():
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--hub-threshold", type=int, default=256, help="degree from which adjacency scores are cached per pass")
     return p.parse_args()
 
 
@@ -89,13 +90,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi takes a moment to print its first row; do not start a short timed region before it."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        rows = [r for (t, r) in self.rows if t0 - 0.02 <= t <= t1 + 0.12]
+        if not rows and self.rows:   # region shorter than the sampling period: take the sample nearest to it
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[1]]
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
@@ -269,7 +278,7 @@ def run_b200(args):
 
     hg, emb_h, roots, d = make_inputs(args, rank)
     dg = G.DeviceGraph(hg, dev)
-    smp = S.WalkSampler(dg)
+    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold)
     emb = S.pad_embedding(emb_h, dev)
     bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
     t0 = time.time()
@@ -336,6 +345,7 @@ def run_b200(args):
         return ms, kern_ms, cnts, t_start, t_end
 
     clocks = ClockSampler(local)
+    clocks.wait_first()
     ms, kern_ms, cnts, t_start, t_end = timed(False)
     clk = clocks.stop(t_start, t_end)
     ms_e2e, _, cnts_e2e, _, _ = timed(True)
@@ -401,7 +411,9 @@ def run_b200(args):
                                  "HBM copy peak by design; executed_* counts the rows it really fetches (DESIGN.md 5)"},
             "walk": {"walks_per_step": W, "steps_per_neg_edge": c0["steps"] / max(c0["accepted"], 1),
                      "cands_per_neg_edge": c0["sum_l"] / max(c0["accepted"], 1), "ok_roots": c0["ok_roots"],
-                     "bfs_build_s": t_bfs},
+                     "bfs_build_s": t_bfs,
+                     "warp_cycle_share": {k[4:]: round(c0[k] / max(c0["cyc_walk"], 1), 4) for k in
+                                          ("cyc_enum", "cyc_score", "cyc_choose", "cyc_step0", "cyc_step1", "cyc_step2p")}},
         }
         if not args.no_cpu_baseline and world >= 1:
             par_dev = trees.parent

@@ -44,8 +44,8 @@ SIGNATURES = {
     "gg_walk_sample": (C.c_int, [C.POINTER(WalkDesc), _P]),
     "gg_walk_finalize": (C.c_int, [_I64, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gg_emit_d_rows": (C.c_int, [_I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "gg_bfs_scratch_bytes": (C.c_int, [_I64, C.POINTER(_I64)]),
-    "gg_bfs_build": (C.c_int, [_I64, _P, _P, _I64, _P, _P, _P, _I64, _P]),
+    "gg_bfs_scratch_bytes": (C.c_int, [_I64, _I64, C.POINTER(_I64)]),
+    "gg_bfs_build": (C.c_int, [_I64, _I64, _P, _P, _I64, _P, _P, _P, _I64, _P]),
     "gg_pair_reward": (C.c_int, [_I64, _P, _P, _P, _P, _I32, _P, _P]),
     "gg_all_score": (C.c_int, [_I64, _P, _P, _I32, _P, _P]),
     "gg_pair_grad": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P]),

@@ -9,13 +9,17 @@
 // The father of v must be the FIRST node, in the reference's FIFO order, that has v in its
 // adjacency.  Level-synchronous formulation: number every (frontier node, adjacency slot)
 // pair of a level consecutively in (frontier order, slot order) -- that number `q` is exactly
-// the order in which the reference's loop would look at the edge -- and let every edge
-// atomicMin its q into claim[v].  The minimum is the reference's discoverer, and the winners
-// sorted by q (a stable compaction) are the next frontier in FIFO order.  q keeps growing
-// across levels, so claim[v] < level_base  <=>  "v was discovered earlier": no separate
-// visited array is needed and already-discovered nodes can never win again.
+// the order in which the reference's loop would look at the edge -- and let every edge whose
+// head is still undiscovered atomicMin its q into claim[head].  The minimum is the reference's
+// discoverer, and the winners in q order (a stable compaction) are the next frontier in FIFO
+// order.  q keeps growing across levels, so a stale claim can never equal a current q.
 //
-// One CTA owns one root at a time.  HBM/L2-bound integer work; no tensor cores.
+// One 1024-thread CTA owns one root at a time.  Per level: (A) prefix sums over the frontier,
+// (B) claim sweep, (C) winner sweep (records one win bit per frontier edge), (D) prefix sum of
+// the winner counts, (E) scatter from the win bits.  A visited bitmap in SHARED memory (N bits;
+// global scratch when N > ~1.7M) filters already-discovered heads, so the only random global
+// accesses are one atomicMin + one 4-byte read per edge into the NEXT level.
+// HBM/L2-bound integer work; no tensor cores.
 #include "gg_common.cuh"
 
 namespace gg {
@@ -23,6 +27,12 @@ namespace {
 
 constexpr int BFS_THREADS = 1024;
 constexpr int BFS_WARPS = BFS_THREADS / 32;
+constexpr long long BFS_SMEM_BITMAP_MAX_BYTES = 200 * 1024;
+
+__host__ __device__ inline long long bfs_words_per_cta(long long n, long long nnz, bool bitmap_in_smem) {
+    const long long bm = bitmap_in_smem ? 0 : (n + 31) / 32;
+    return 7 * n + nnz / 32 + bm + 8;
+}
 
 // exclusive scan of f(i), i in [0,n), into out[0..n]; returns total (block-wide, all threads).
 template <typename F>
@@ -64,50 +74,81 @@ __device__ unsigned block_exclusive_scan(F f, unsigned *out, unsigned n, unsigne
 }
 
 __global__ void __launch_bounds__(BFS_THREADS, 1)
-bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__restrict__ adj, long long n_roots,
-           const int *__restrict__ roots, int *__restrict__ parent, unsigned *__restrict__ scratch) {
+bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr, const int *__restrict__ adj,
+           long long n_roots, const int *__restrict__ roots, int *__restrict__ parent, unsigned *__restrict__ scratch,
+           int bitmap_in_smem) {
+    extern __shared__ unsigned s_bitmap[];
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t N = (size_t)n_node;
-    unsigned *claim = scratch + (size_t)blockIdx.x * (5 * N + 2);
+    const size_t bm_words = (N + 31) / 32;
+    unsigned *claim = scratch + (size_t)blockIdx.x * (size_t)bfs_words_per_cta(n_node, nnz, bitmap_in_smem != 0);
     int *fa = reinterpret_cast<int *>(claim + N);
     int *fb = fa + N;
-    unsigned *off = reinterpret_cast<unsigned *>(fb + N);  // [N+1]
-    unsigned *base = off + N + 1;                           // [N+1]
+    unsigned *off = reinterpret_cast<unsigned *>(fb + N);   // [N+1] q numbering
+    unsigned *base = off + N + 1;                            // [N+1] winners per frontier node / compaction offsets
+    unsigned *woff = base + N + 1;                           // [N+1] first win-mask word of a frontier node
+    unsigned *wmask = woff + N + 1;                          // [nnz/32 + N + 1]
+    unsigned *bm = bitmap_in_smem ? s_bitmap : (wmask + nnz / 32 + N + 1);
 
     for (long long r = blockIdx.x; r < n_roots; r += gridDim.x) {
         const int root = roots[r];
         int *par = parent + (size_t)r * N;
         for (size_t i = threadIdx.x; i < N; i += BFS_THREADS) { claim[i] = 0xffffffffu; par[i] = -1; }
+        for (size_t i = threadIdx.x; i < bm_words; i += BFS_THREADS) bm[i] = 0u;
         __syncthreads();
-        if (threadIdx.x == 0) { claim[root] = 0u; fa[0] = root; }
+        if (threadIdx.x == 0) { bm[root >> 5] |= 1u << (root & 31); fa[0] = root; }
         __syncthreads();
         unsigned nf = 1, level_base = 1;
         int *cur = fa, *nxt = fb;
         while (nf > 0) {
-            // A: q numbering = exclusive prefix of the frontier degrees
+            // A: q numbering and win-mask word numbering = prefix sums over the frontier
             const unsigned n_edges = block_exclusive_scan(
                 [&](unsigned i) { const int u = cur[i]; return (unsigned)(indptr[u + 1] - indptr[u]); }, off, nf, s_warp,
                 &s_carry);
-            // B: every frontier edge claims its head with its visit order
+            block_exclusive_scan(
+                [&](unsigned i) { const int u = cur[i]; return (unsigned)((indptr[u + 1] - indptr[u] + 31) >> 5); }, woff, nf,
+                s_warp, &s_carry);
+            // B: every frontier edge with an undiscovered head claims it with its visit order
             for (unsigned i = wid; i < nf; i += BFS_WARPS) {
                 const int u = cur[i];
                 const long long a0 = indptr[u];
                 const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
-                for (unsigned j = lane; j < dg; j += 32) atomicMin(claim + adj[a0 + j], q0 + j);
+                for (unsigned j0 = 0; j0 < dg; j0 += 128) {
+                    int v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const unsigned j = j0 + 32 * k + lane; v[k] = (j < dg) ? __ldg(adj + a0 + j) : -1; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (v[k] >= 0 && !((bm[v[k] >> 5] >> (v[k] & 31)) & 1u)) atomicMin(claim + v[k], q0 + j0 + 32 * k + lane);
+                }
             }
             __syncthreads();
-            // C: winners per frontier node
+            // C: winners per frontier node, one win bit per edge
             for (unsigned i = wid; i < nf; i += BFS_WARPS) {
                 const int u = cur[i];
                 const long long a0 = indptr[u];
-                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
+                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i], w0 = woff[i];
                 unsigned c = 0;
-                for (unsigned j0 = 0; j0 < dg; j0 += 32) {
-                    const unsigned j = j0 + lane;
-                    const bool win = (j < dg) && (__ldcg(claim + adj[a0 + j]) == q0 + j);
-                    c += __popc(__ballot_sync(FULL, win));
+                for (unsigned j0 = 0; j0 < dg; j0 += 128) {
+                    int v[4];
+                    bool cand[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const unsigned j = j0 + 32 * k + lane; v[k] = (j < dg) ? __ldg(adj + a0 + j) : -1; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cand[k] = v[k] >= 0 && !((bm[v[k] >> 5] >> (v[k] & 31)) & 1u);
+                    unsigned cl[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) cl[k] = cand[k] ? __ldcg(claim + v[k]) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned mk = __ballot_sync(FULL, cand[k] && cl[k] == q0 + j0 + 32 * k + lane);
+                        if (j0 + 32 * k < dg) {
+                            if (lane == 0) wmask[w0 + (j0 >> 5) + k] = mk;
+                            c += __popc(mk);
+                        }
+                    }
                 }
                 if (lane == 0) base[i] = c;
             }
@@ -118,15 +159,18 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
             for (unsigned i = wid; i < nf; i += BFS_WARPS) {
                 const int u = cur[i];
                 const long long a0 = indptr[u];
-                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
+                const unsigned dg = (unsigned)(indptr[u + 1] - a0), w0 = woff[i];
                 unsigned o = base[i];
+                if (base[i + 1] == o) continue;   // no winner under this node
                 for (unsigned j0 = 0; j0 < dg; j0 += 32) {
-                    const unsigned j = j0 + lane;
-                    int v = -1;
-                    bool win = false;
-                    if (j < dg) { v = adj[a0 + j]; win = (__ldcg(claim + v) == q0 + j); }
-                    const unsigned mk = __ballot_sync(FULL, win);
-                    if (win) { nxt[o + __popc(mk & ((1u << lane) - 1u))] = v; par[v] = u; }
+                    const unsigned mk = wmask[w0 + (j0 >> 5)];
+                    if (mk == 0u) continue;
+                    if ((mk >> lane) & 1u) {
+                        const int v = __ldg(adj + a0 + j0 + lane);
+                        nxt[o + __popc(mk & ((1u << lane) - 1u))] = v;
+                        par[v] = u;
+                        atomicOr(bm + (v >> 5), 1u << (v & 31));
+                    }
                     o += __popc(mk);
                 }
             }
@@ -142,22 +186,29 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
 }  // namespace
 }  // namespace gg
 
-extern "C" int gg_bfs_scratch_bytes(int64_t n_node, int64_t *bytes) {
-    GG_REQUIRE(bytes && n_node >= 0, "bad arguments");
-    *bytes = (int64_t)gg::sm_count() * (5 * n_node + 2) * 4;
+extern "C" int gg_bfs_scratch_bytes(int64_t n_node, int64_t nnz, int64_t *bytes) {
+    GG_REQUIRE(bytes && n_node >= 0 && nnz >= 0, "bad arguments");
+    const bool in_smem = (n_node + 31) / 32 * 4 <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
+    *bytes = (int64_t)gg::sm_count() * gg::bfs_words_per_cta(n_node, nnz, in_smem) * 4;
     return 0;
 }
 
-extern "C" int gg_bfs_build(int64_t n_node, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
+extern "C" int gg_bfs_build(int64_t n_node, int64_t nnz, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
                             const int32_t *roots, int32_t *parent, void *scratch, int64_t scratch_bytes, void *stream) {
     GG_REQUIRE(indptr && adj && roots && parent && scratch, "null pointer");
+    GG_REQUIRE(nnz < 0xfffffff0ll, "too many edges for 32-bit visit numbers");
     if (n_roots == 0 || n_node == 0) return 0;
-    const int64_t per_cta = (5 * n_node + 2) * 4;
+    const long long bm_bytes = (n_node + 31) / 32 * 4;
+    const bool in_smem = bm_bytes <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
+    const int64_t per_cta = gg::bfs_words_per_cta(n_node, nnz, in_smem) * 4;
     int64_t ctas = scratch_bytes / per_cta;
     if (ctas > gg::sm_count()) ctas = gg::sm_count();
     if (ctas > n_roots) ctas = n_roots;
     GG_REQUIRE(ctas >= 1, "scratch too small");
-    gg::bfs_kernel<<<(unsigned)ctas, gg::BFS_THREADS, 0, (cudaStream_t)stream>>>(
-        n_node, (const long long *)indptr, adj, n_roots, roots, parent, (unsigned *)scratch);
+    const size_t smem = in_smem ? (size_t)bm_bytes : 0;
+    if (smem > 48 * 1024)
+        GG_CHECK(cudaFuncSetAttribute(gg::bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gg::bfs_kernel<<<(unsigned)ctas, gg::BFS_THREADS, smem, (cudaStream_t)stream>>>(
+        n_node, nnz, (const long long *)indptr, adj, n_roots, roots, parent, (unsigned *)scratch, in_smem ? 1 : 0);
     return gg::check_cuda(cudaGetLastError(), "bfs kernel launch");
 }

@@ -40,7 +40,8 @@ template <int CPL>
 __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slot, uint32_t k, long long w,
                                         int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
                                         unsigned long long &raw_steps, unsigned long long &raw_suml,
-                                        unsigned long long &overflow, unsigned long long &rows_gathered) {
+                                        unsigned long long &overflow, unsigned long long &rows_gathered,
+                                        unsigned int (&cyc)[7]) {
     const int root = d.roots[slot];
     const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
     const int ld = d.ld;
@@ -50,7 +51,9 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
     if (prow && lane == 0) prow[0] = cur;
     plen = 1;
 
+    const long long t_walk = clock64();
     for (;;) {
+        const long long t_step = clock64();
         const long long a0 = d.indptr[cur], a1 = d.indptr[cur + 1];
         int n, idx, nxt;
         bool inc_father = false;
@@ -76,6 +79,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
             float m = -INFINITY;   // running max of the cached scores (lane local)
             const unsigned lt = (1u << lane) - 1u;
+            const long long t_e = clock64();
             for (long long e0 = a0; e0 < a1; e0 += 32 * UNR) {   // UNR adjacency tiles in flight
                 int v[UNR], p[UNR];
                 float cs[UNR];
@@ -100,6 +104,8 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
                 }
             }
             __syncwarp();
+            const long long t_s = clock64();
+            cyc[0] += (unsigned int)(t_s - t_e);
             if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
 
             // ---- scores: all_score[cur, cand] (generator.py:21), canonical dot
@@ -117,12 +123,16 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             }
 
             // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
+            const long long t_c = clock64();
+            cyc[1] += (unsigned int)(t_c - t_s);
             const double u = rng.draw((uint32_t)root, k, (uint32_t)step);
             if (rng.exhausted) { status = GG_NOTRUN; break; }
             idx = choose_index(sc, n, m, u, lane);
             nxt = ids[idx];
             __syncwarp();
+            cyc[2] += (unsigned int)(clock64() - t_c);
         }
+        cyc[step == 0 ? 3 : (step == 1 ? 4 : 5)] += (unsigned int)(clock64() - t_step);
         if (step == 0) fedge = (int)(a0 + idx);  // every walk-CSR neighbour of the root is its child
         if (prow && lane == 0 && plen < d.max_path) prow[plen] = nxt;
         ++plen;
@@ -130,6 +140,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
         if (inc_father && idx == 0) { sample = cur; status = GG_DONE; break; }  // graph_gan.py:264-266
         prev = cur; cur = nxt; ++step;
     }
+    cyc[6] += (unsigned int)(clock64() - t_walk);
     raw_steps += (unsigned)steps; raw_suml += (unsigned)suml;
     if (lane == 0) {
         d.samples[w] = sample;
@@ -157,6 +168,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_kernel(const __gri
     rng.mode = GG_RNG_PHILOX; rng.k0 = (uint32_t)d.seed; rng.k1 = (uint32_t)(d.seed >> 32); rng.tag = d.pass_tag;
     rng.stream = nullptr; rng.n_stream = 0; rng.cursor = 0; rng.exhausted = 0;
     unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
+    unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool ratio_all = d.update_ratio >= 1.0;
 
     for (;;) {
@@ -184,9 +196,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_kernel(const __gri
                 continue;
             }
         }
-        walk_one<CPL>(d, rng, slot, k, w, s_ids, s_sc, g_ids, g_sc, lane, raw_steps, raw_suml, overflow, rows_gathered);
+        walk_one<CPL>(d, rng, slot, k, w, s_ids, s_sc, g_ids, g_sc, lane, raw_steps, raw_suml, overflow, rows_gathered,
+                      cyc);
     }
     if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) if (cyc[q]) atomicAdd(d.counters + GG_CNT_CYC_ENUM + q, (unsigned long long)cyc[q]);
         if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
         if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
         if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
@@ -209,6 +224,7 @@ __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__
     rng.mode = GG_RNG_STREAM; rng.k0 = rng.k1 = rng.tag = 0;
     rng.stream = d.stream; rng.n_stream = d.n_stream; rng.cursor = 0; rng.exhausted = 0;
     unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
+    unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
     for (long long slot = 0; slot < d.n_roots && !rng.exhausted; ++slot) {
         const long long w0 = d.walk_ptr[slot], w1 = d.walk_ptr[slot + 1];
         const double ur = rng.draw(0, 0, 0);
@@ -224,7 +240,7 @@ __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__
                 continue;
             }
             const int st = walk_one<CPL>(d, rng, (int)slot, (uint32_t)(w - w0), w, s_ids, s_sc, g_ids, g_sc, lane,
-                                         raw_steps, raw_suml, overflow, rows_gathered);
+                                         raw_steps, raw_suml, overflow, rows_gathered, cyc);
             if (st != GG_DONE) dead = true;
         }
     }

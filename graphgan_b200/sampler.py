@@ -15,7 +15,7 @@ from ._cabi import ptr
 RNG_PHILOX, RNG_STREAM = 0, 1
 NOTRUN, DONE, VOID, SKIPPED = 0, 1, 2, 3
 CNT = dict(steps=0, sum_l=1, accepted=2, ok_roots=3, path_overflow=4, raw_steps=5, raw_sum_l=6, stream_used=7,
-           rows_gathered=8)
+           rows_gathered=8, cyc_enum=9, cyc_score=10, cyc_choose=11, cyc_step0=12, cyc_step1=13, cyc_step2p=14, cyc_walk=15)
 
 
 def round_up(x, m):
@@ -81,7 +81,7 @@ class WalkPlan:
         self.paths = i32(W, max_path) if max_path > 0 else None
         self.path_len = i32(W) if max_path > 0 else None
         self.root_ok = torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
-        self.counters = torch.zeros(12, dtype=torch.int64, device=dev)
+        self.counters = torch.zeros(16, dtype=torch.int64, device=dev)
         self.row_ptr = torch.empty(R + 1, dtype=torch.int64, device=dev)
         self.n_rows = torch.zeros(1, dtype=torch.int64, device=dev)
         self.rows = [i32(max(2 * self.n_walks, 1)) for _ in range(3)] if for_d else None
@@ -114,9 +114,9 @@ class WalkSampler:
         parent = torch.empty((R, N), dtype=torch.int32, device=self.device)
         if self._bfs_scratch is None:
             nbytes = C.c_int64(0)
-            _cabi.check(self.lib.gg_bfs_scratch_bytes(N, C.byref(nbytes)), "gg_bfs_scratch_bytes")
+            _cabi.check(self.lib.gg_bfs_scratch_bytes(N, int(self.g.adj.shape[0]), C.byref(nbytes)), "gg_bfs_scratch_bytes")
             self._bfs_scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
-        _cabi.check(self.lib.gg_bfs_build(N, ptr(self.g.indptr), ptr(self.g.adj), R, ptr(roots_d), ptr(parent),
+        _cabi.check(self.lib.gg_bfs_build(N, int(self.g.adj.shape[0]), ptr(self.g.indptr), ptr(self.g.adj), R, ptr(roots_d), ptr(parent),
                                           ptr(self._bfs_scratch), self._bfs_scratch.numel(), self._stream()), "gg_bfs_build")
         return TreeBatch(roots_d, parent)
 

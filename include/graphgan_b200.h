@@ -43,7 +43,10 @@ enum {
     GG_CNT_STEPS = 0, GG_CNT_SUML = 1, GG_CNT_ACCEPTED = 2, GG_CNT_OK_ROOTS = 3,
     GG_CNT_PATH_OVERFLOW = 4, GG_CNT_RAW_STEPS = 5, GG_CNT_RAW_SUML = 6, GG_CNT_STREAM_USED = 7,
     GG_CNT_ROWS_GATHERED = 8, /* embedding rows the walk kernel actually fetched (on-demand scores + cur rows) */
-    GG_CNT_SLOTS = 12
+    /* warp-cycles (clock64, summed over warps) spent per phase of the walk kernel */
+    GG_CNT_CYC_ENUM = 9, GG_CNT_CYC_SCORE = 10, GG_CNT_CYC_CHOOSE = 11, GG_CNT_CYC_STEP0 = 12,
+    GG_CNT_CYC_STEP1 = 13, GG_CNT_CYC_STEP2P = 14, GG_CNT_CYC_WALK = 15,
+    GG_CNT_SLOTS = 16
 };
 
 const char *gg_last_error(void);
@@ -137,8 +140,8 @@ int gg_emit_d_rows(int64_t n_roots, const int32_t *roots, const int64_t *walk_pt
  * Tree construction: GraphGAN.construct_trees (graph_gan.py:84-108) for a batch of roots, as
  * parent arrays (first discoverer in FIFO / adjacency order).  parent: device [R, N].
  * ------------------------------------------------------------------------------------------ */
-int gg_bfs_scratch_bytes(int64_t n_node, int64_t *bytes);
-int gg_bfs_build(int64_t n_node, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
+int gg_bfs_scratch_bytes(int64_t n_node, int64_t nnz, int64_t *bytes);
+int gg_bfs_build(int64_t n_node, int64_t nnz, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
                  const int32_t *roots, int32_t *parent, void *scratch, int64_t scratch_bytes,
                  void *stream);
 

@@ -40,7 +40,7 @@ def test_cabi_argument_errors_do_not_abort():
     assert lib.gg_walk_sample(None, None) != 0
     assert lib.gg_pair_grad(7, 1, 0, None, None, None, None, None, 32, C.c_float(0), None, None, None, None, None, None) != 0
     with pytest.raises(_cabi.GGError):
-        _cabi.check(lib.gg_bfs_build(10, None, None, 1, None, None, None, 0, None), "gg_bfs_build")
+        _cabi.check(lib.gg_bfs_build(10, 20, None, None, 1, None, None, None, 0, None), "gg_bfs_build")
 
 
 def test_product_does_not_import_oracle():
