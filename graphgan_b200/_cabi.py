@@ -29,7 +29,8 @@ class WalkDesc(C.Structure):
         ("wsuml", C.c_void_p), ("paths", C.c_void_p), ("path_len", C.c_void_p), ("counters", C.c_void_p),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64), ("work_counter", C.c_void_p),
         ("edge_score", C.c_void_p), ("root_q", C.c_void_p), ("rq_ptr", C.c_void_p),
-        ("hub_threshold", C.c_int32), ("reserved2", C.c_int32),
+        ("hub_threshold", C.c_int32), ("chunk_walks", C.c_int32),
+        ("chunk_ptr", C.c_void_p), ("n_chunks", C.c_int64), ("walk_slot", C.c_void_p),
     ]
 
 
@@ -52,6 +53,8 @@ SIGNATURES = {
     "gg_grad_buf_floats": (_I64, [_I32, _I32]),
     "gg_grad_merge": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "gg_adam_apply": (C.c_int, [_I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),
+    "gg_train_steps": (C.c_int, [_I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P,
+                                _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "gg_window_pairs": (C.c_int, [_I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _P]),
 }
 

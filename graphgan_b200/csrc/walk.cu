@@ -35,6 +35,74 @@ struct Rng {
     }
 };
 
+// Candidate list of `cur` in the tree of the root whose parent array is `par` (graph_gan.py:250-259):
+// [father] + children in adjacency order, with scores all_score[cur, cand] (generator.py:21) -- cached hub
+// scores or the on-demand canonical dot -- and their max.  Warp-cooperative; results are warp-uniform.
+template <int CPL>
+__device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t *__restrict__ par, int cur, int prev,
+                                           bool inc_father, int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
+                                           int &n_out, float &m_out, int *&ids_out, float *&sc_out,
+                                           unsigned long long &rows_gathered, unsigned int (&cyc)[7]) {
+    const long long a0 = d.indptr[cur], a1 = d.indptr[cur + 1];
+    const bool cached = d.edge_score && (a1 - a0) >= d.hub_threshold;  // scores precomputed per pass
+    int *ids = (a1 - a0 + 1) <= ID_CAP ? s_ids : g_ids;
+    float *sc = (a1 - a0 + 1) <= SC_CAP ? s_sc : g_sc;
+    int n = 0;
+    if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
+    float m = -INFINITY;   // running max of the cached scores (lane local)
+    const unsigned lt = (1u << lane) - 1u;
+    const long long t_e = clock64();
+    for (long long e0 = a0; e0 < a1; e0 += 32 * UNR) {   // UNR adjacency tiles in flight
+        int v[UNR], p[UNR];
+        float cs[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const long long e = e0 + 32 * k + lane;
+            v[k] = (e < a1) ? __ldg(d.adj + e) : -1;
+            cs[k] = (cached && e < a1) ? __ldg(d.edge_score + e) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) p[k] = (v[k] >= 0) ? __ldg(par + v[k]) : -2;
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const bool isc = p[k] == cur;
+            const unsigned mk = __ballot_sync(FULL, isc);
+            if (isc) {
+                const int pos = n + __popc(mk & lt);
+                ids[pos] = v[k];
+                if (cached) {
+                    sc[pos] = cs[k]; m = fmaxf(m, cs[k]);
+                } else {
+                    // the row will be scored on demand in a moment: start its DRAM fetch now, for all
+                    // candidates at once (the scoring loop itself only keeps 8 rows in flight per warp)
+                    const float *row = d.emb + (size_t)v[k] * (size_t)d.ld;
+                    for (int b = 0; b < d.ld; b += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+                }
+            }
+            n += __popc(mk);
+        }
+    }
+    __syncwarp();
+    const long long t_s = clock64();
+    cyc[0] += (unsigned int)(t_s - t_e);
+    n_out = n; ids_out = ids; sc_out = sc; m_out = m;
+    if (n == 0) return;
+    if (!cached || inc_father) {
+        float4 c4[CPL];
+        load_row<CPL>(d.emb, d.ld, cur, lane & 7, c4);
+        score_list<CPL>(d.emb, d.bias, d.ld, c4, ids, sc, cached ? 1 : n, cur, lane);
+        rows_gathered += 1u + (unsigned)(cached ? 1 : n);
+    }
+    if (cached) {
+        m = warp_max(m);
+        if (inc_father) m = fmaxf(m, sc[0]);
+    } else {
+        m = (sc == s_sc) ? list_max<true>(sc, n, lane) : list_max<false>(sc, n, lane);
+    }
+    m_out = m;
+    cyc[1] += (unsigned int)(clock64() - t_s);
+}
+
 // One complete walk, executed by a full warp.  Returns the status.
 template <int CPL>
 __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slot, uint32_t k, long long w,
@@ -44,7 +112,6 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
                                         unsigned int (&cyc)[7]) {
     const int root = d.roots[slot];
     const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
-    const int ld = d.ld;
     int cur = root, prev = -1, step = 0, fedge = -1, plen = 0;
     int steps = 0, suml = 0, status = GG_NOTRUN, sample = -1;
     int32_t *prow = (d.max_path > 0 && d.paths) ? d.paths + (size_t)w * (size_t)d.max_path : nullptr;
@@ -68,66 +135,19 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             idx = cdf_search(d.root_q + __ldg(d.rq_ptr + slot), n, u);
             nxt = __ldg(d.adj + a0 + idx);
         } else {
-            // ---- candidate list (graph_gan.py:250-259)
+            // ---- candidate list (graph_gan.py:250-259) + scores
             inc_father = step > 0;
             if (d.for_d && step == 1) inc_father = false;
             if (!d.for_d && step == 1 && ((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u)) inc_father = false;
-            const bool cached = d.edge_score && (a1 - a0) >= d.hub_threshold;  // scores precomputed per pass
-            int *ids = (a1 - a0 + 1) <= ID_CAP ? s_ids : g_ids;
-            float *sc = (a1 - a0 + 1) <= SC_CAP ? s_sc : g_sc;
-            n = 0;
-            if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
-            float m = -INFINITY;   // running max of the cached scores (lane local)
-            const unsigned lt = (1u << lane) - 1u;
-            const long long t_e = clock64();
-            for (long long e0 = a0; e0 < a1; e0 += 32 * UNR) {   // UNR adjacency tiles in flight
-                int v[UNR], p[UNR];
-                float cs[UNR];
-#pragma unroll
-                for (int k = 0; k < UNR; ++k) {
-                    const long long e = e0 + 32 * k + lane;
-                    v[k] = (e < a1) ? __ldg(d.adj + e) : -1;
-                    cs[k] = (cached && e < a1) ? __ldg(d.edge_score + e) : 0.0f;
-                }
-#pragma unroll
-                for (int k = 0; k < UNR; ++k) p[k] = (v[k] >= 0) ? __ldg(par + v[k]) : -2;
-#pragma unroll
-                for (int k = 0; k < UNR; ++k) {
-                    const bool isc = p[k] == cur;
-                    const unsigned mk = __ballot_sync(FULL, isc);
-                    if (isc) {
-                        const int pos = n + __popc(mk & lt);
-                        ids[pos] = v[k];
-                        if (cached) { sc[pos] = cs[k]; m = fmaxf(m, cs[k]); }
-                    }
-                    n += __popc(mk);
-                }
-            }
-            __syncwarp();
-            const long long t_s = clock64();
-            cyc[0] += (unsigned int)(t_s - t_e);
+            int *ids; float *sc; float m;
+            build_list<CPL>(d, par, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
             if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
-
-            // ---- scores: all_score[cur, cand] (generator.py:21), canonical dot
-            if (!cached || inc_father) {
-                float4 c4[CPL];
-                load_row<CPL>(d.emb, ld, cur, lane & 7, c4);
-                score_list<CPL>(d.emb, d.bias, ld, c4, ids, sc, cached ? 1 : n, cur, lane);
-                rows_gathered += 1u + (unsigned)(cached ? 1 : n);
-            }
-            if (cached) {
-                m = warp_max(m);
-                if (inc_father) m = fmaxf(m, sc[0]);
-            } else {
-                m = list_max(sc, n, lane);
-            }
 
             // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
             const long long t_c = clock64();
-            cyc[1] += (unsigned int)(t_c - t_s);
             const double u = rng.draw((uint32_t)root, k, (uint32_t)step);
             if (rng.exhausted) { status = GG_NOTRUN; break; }
-            idx = choose_index(sc, n, m, u, lane);
+            idx = (sc == s_sc) ? choose_index<true>(sc, n, m, u, lane) : choose_index<false>(sc, n, m, u, lane);
             nxt = ids[idx];
             __syncwarp();
             cyc[2] += (unsigned int)(clock64() - t_c);
@@ -177,13 +197,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_kernel(const __gri
         wi = __shfl_sync(FULL, wi, 0);
         const long long w = wi;
         if (w >= d.n_walks) break;
-        // walk -> root slot: last slot with walk_ptr[slot] <= w
-        long long lo = 0, hi = d.n_roots;
-        while (hi - lo > 1) {
-            const long long mid = (lo + hi) >> 1;
-            if (__ldg(d.walk_ptr + mid) <= w) lo = mid; else hi = mid;
+        // walk -> root slot: last slot with walk_ptr[slot] <= w (table when the caller provides one)
+        int slot;
+        if (d.walk_slot) {
+            slot = __ldg(d.walk_slot + w);
+        } else {
+            long long lo = 0, hi = d.n_roots;
+            while (hi - lo > 1) {
+                const long long mid = (lo + hi) >> 1;
+                if (__ldg(d.walk_ptr + mid) <= w) lo = mid; else hi = mid;
+            }
+            slot = (int)lo;
         }
-        const int slot = (int)lo;
         const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
         if (!ratio_all) {  // graph_gan.py:189/209: one draw per root
             uint32_t a, b;
@@ -198,6 +223,149 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_kernel(const __gri
         }
         walk_one<CPL>(d, rng, slot, k, w, s_ids, s_sc, g_ids, g_sc, lane, raw_steps, raw_suml, overflow, rows_gathered,
                       cyc);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) if (cyc[q]) atomicAdd(d.counters + GG_CNT_CYC_ENUM + q, (unsigned long long)cyc[q]);
+        if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
+        if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
+        if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
+        if (rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
+    }
+}
+
+// ---------------------------------------------------------------- chunked order-free kernel
+// One warp owns a CHUNK of up to 32 walks of the same root (lane <-> walk for the bookkeeping) and advances
+// them together: walks of the chunk that stand on the same node share ONE candidate list / softmax / CDF
+// (the heavy, warp-cooperative part) and only differ in their uniform draw.  With sample_num = deg(root)
+// walks per root and a peaked softmax most walks of a chunk share their first nodes, which removes most of
+// the redundant list constructions; the draws stay keyed by (root, walk, step), so results are unchanged.
+constexpr int RUNNING = -1;
+
+template <int CPL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_chunk_kernel(const __grid_constant__ gg_walk_desc d) {
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
+    int *s_ids = reinterpret_cast<int *>(s_sc + SC_CAP);
+    const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
+    int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
+    float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
+    const uint32_t k0key = (uint32_t)d.seed, k1key = (uint32_t)(d.seed >> 32);
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
+    unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const bool ratio_all = d.update_ratio >= 1.0;
+
+    for (;;) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(d.work_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if ((long long)item >= d.n_chunks) break;
+        const long long t_walk = clock64();
+        long long lo = 0, hi = d.n_roots;   // chunk -> root slot: last slot with chunk_ptr[slot] <= item
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (__ldg(d.chunk_ptr + mid) <= (long long)item) lo = mid; else hi = mid;
+        }
+        const int slot = (int)lo;
+        const long long w0 = __ldg(d.walk_ptr + slot), nw = __ldg(d.walk_ptr + slot + 1) - w0;
+        const int cw = d.chunk_walks;
+        const long long kbase = ((long long)item - __ldg(d.chunk_ptr + slot)) * cw;
+        const int cnt = (int)((nw - kbase) < cw ? (nw - kbase) : cw);
+        const bool mine = lane < cnt;
+        const uint32_t k = (uint32_t)(kbase + lane);
+        const long long w = w0 + kbase + lane;
+        const int root = d.roots[slot];
+        const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
+        int32_t *prow = (mine && d.max_path > 0 && d.paths) ? d.paths + (size_t)w * (size_t)d.max_path : nullptr;
+        if (!ratio_all) {  // graph_gan.py:189/209: one draw per root
+            uint32_t a, b;
+            philox4x32_10((uint32_t)root, 0xffffffffu, 0u, d.pass_tag, k0key, k1key, a, b);
+            if (!(u53(a, b) < d.update_ratio)) {
+                if (mine) {
+                    d.samples[w] = -1; d.status[w] = GG_SKIPPED; d.first_edge[w] = -1; d.wsteps[w] = 0; d.wsuml[w] = 0;
+                    if (d.path_len) d.path_len[w] = 0;
+                }
+                continue;
+            }
+        }
+        int cur = root, prev = -1, step = 0, fedge = -1, steps = 0, suml = 0, plen = 1, sample = -1;
+        int status = mine ? RUNNING : GG_NOTRUN;
+        if (prow) prow[0] = root;
+        const long long a0r = d.indptr[root], a1r = d.indptr[root + 1];
+        if (d.root_q) {   // root step: every lane inverts the root's precomputed CDF for its own walk
+            const long long t0 = clock64();
+            const int n0 = (int)(a1r - a0r);
+            if (n0 == 0) {
+                if (mine) status = GG_VOID;   // graph_gan.py:252-253
+            } else if (mine) {
+                uint32_t a, b;
+                philox4x32_10((uint32_t)root, k, 0u, d.pass_tag, k0key, k1key, a, b);
+                const int idx = cdf_search(d.root_q + __ldg(d.rq_ptr + slot), n0, u53(a, b));
+                const int nxt = __ldg(d.adj + a0r + idx);
+                fedge = (int)(a0r + idx);
+                if (prow && plen < d.max_path) prow[plen] = nxt;
+                plen = 2; steps = 1; suml = n0; prev = root; cur = nxt; step = 1;
+            }
+            __syncwarp();
+            cyc[3] += (unsigned int)(clock64() - t0);
+        }
+        for (;;) {
+            const unsigned running = __ballot_sync(FULL, status == RUNNING);
+            if (!running) break;
+            const long long t_step = clock64();
+            const int leader = __ffs(running) - 1;
+            const int ccur = __shfl_sync(FULL, cur, leader), cstep = __shfl_sync(FULL, step, leader);
+            const int cprev = __shfl_sync(FULL, prev, leader), cfedge = __shfl_sync(FULL, fedge, leader);
+            const unsigned grp = __ballot_sync(FULL, status == RUNNING && cur == ccur);
+            bool inc_father = cstep > 0;
+            if (d.for_d && cstep == 1) inc_father = false;
+            if (!d.for_d && cstep == 1 && ((d.d1_bits[cfedge >> 5] >> (cfedge & 31)) & 1u)) inc_father = false;
+            int n; float m; int *ids; float *sc;
+            build_list<CPL>(d, par, ccur, cprev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
+            if (n == 0) {   // graph_gan.py:252-257
+                if ((grp >> lane) & 1u) status = GG_VOID;
+            } else {
+                const long long t_c = clock64();
+                const bool sh = (sc == s_sc);
+                const float S = sh ? softmax_exp_sum<true>(sc, n, m, lane) : softmax_exp_sum<false>(sc, n, m, lane);
+                double car[2];
+                const double total = sh ? cdf_total<true>(sc, n, S, lane, car) : cdf_total<false>(sc, n, S, lane, car);
+                const long long a0c = d.indptr[ccur];
+                for (unsigned rest = grp; rest; rest &= rest - 1u) {
+                    const int j = __ffs(rest) - 1;
+                    const uint32_t kj = __shfl_sync(FULL, k, j);
+                    uint32_t a, b;
+                    philox4x32_10((uint32_t)root, kj, (uint32_t)cstep, d.pass_tag, k0key, k1key, a, b);
+                    const int idx = sh ? cdf_pick<true>(sc, n, S, total, u53(a, b), lane, car)
+                                       : cdf_pick<false>(sc, n, S, total, u53(a, b), lane, car);
+                    const int nxt = ids[idx];
+                    if (lane == j) {
+                        if (cstep == 0) fedge = (int)(a0c + idx);
+                        if (prow && plen < d.max_path) prow[plen] = nxt;
+                        ++plen; ++steps; suml += n;
+                        if (inc_father && idx == 0) { sample = cur; status = GG_DONE; }   // graph_gan.py:264-266
+                        else { prev = cur; cur = nxt; ++step; }
+                    }
+                }
+                __syncwarp();
+                cyc[2] += (unsigned int)(clock64() - t_c);
+            }
+            cyc[cstep == 0 ? 3 : (cstep == 1 ? 4 : 5)] += (unsigned int)(clock64() - t_step);
+        }
+        if (mine) {
+            d.samples[w] = sample; d.status[w] = status; d.first_edge[w] = fedge; d.wsteps[w] = steps; d.wsuml[w] = suml;
+            if (d.path_len) d.path_len[w] = (status == GG_DONE) ? plen : 0;
+            raw_steps += (unsigned)steps; raw_suml += (unsigned)suml;
+            if (status == GG_DONE && d.max_path > 0 && plen > d.max_path) overflow += 1;
+        }
+        cyc[6] += (unsigned int)(clock64() - t_walk);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        raw_steps += __shfl_xor_sync(FULL, raw_steps, off);
+        raw_suml += __shfl_xor_sync(FULL, raw_suml, off);
+        overflow += __shfl_xor_sync(FULL, overflow, off);
     }
     if (lane == 0) {
 #pragma unroll
@@ -368,6 +536,24 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
     } else {
         const int ctas = gg::grid_ctas();
         GG_REQUIRE(d.scratch_bytes >= (int64_t)ctas * gg::WARPS_PER_CTA * 2 * d.max_cand * 4, "scratch too small");
+        if (d.chunk_ptr) {
+            GG_REQUIRE(d.n_chunks >= 0 && d.n_chunks < (1ll << 32), "bad chunk count");
+            GG_REQUIRE(d.chunk_walks >= 1 && d.chunk_walks <= 32, "chunk_walks must be in [1, 32]");
+            if (d.n_chunks == 0) return 0;
+#define GG_CHUNK(C)                                                                                                   \
+    GG_CHECK(cudaFuncSetAttribute(gg::walk_chunk_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                  gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                      \
+    gg::walk_chunk_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d)
+            switch (cpl) {
+                case 1: GG_CHUNK(1); break;
+                case 2: GG_CHUNK(2); break;
+                case 4: GG_CHUNK(4); break;
+                case 8: GG_CHUNK(8); break;
+                default: gg::set_error("gg_walk_sample: unsupported ld %d (supported: 32, 64, 128, 256)", d.ld); return 2;
+            }
+#undef GG_CHUNK
+            return gg::check_cuda(cudaGetLastError(), "walk chunk kernel launch");
+        }
         switch (cpl) {
 #define GG_WALK(C)                                                                                                    \
     GG_CHECK(cudaFuncSetAttribute(gg::walk_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \

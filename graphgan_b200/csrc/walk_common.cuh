@@ -88,27 +88,49 @@ __device__ __forceinline__ void score_edges(const float *__restrict__ emb, const
     __syncwarp();
 }
 
+// The score buffer is either this warp's shared-memory slice or its global scratch.  Going through a generic
+// pointer makes every access a generic LD/ST (long-scoreboard latency even when it lands in shared memory), so
+// the passes below are instantiated for both address spaces and use LDS/STS on the shared path.
+template <bool SH> __device__ __forceinline__ float buf_ld(const float *p, int i) {
+    if constexpr (SH) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p + i)));
+        return v;
+    } else {
+        return p[i];
+    }
+}
+template <bool SH> __device__ __forceinline__ void buf_st(float *p, int i, float v) {
+    if constexpr (SH) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p + i)), "f"(v));
+    } else {
+        p[i] = v;
+    }
+}
+
 // max over sc[0..n)
+template <bool SH>
 __device__ __forceinline__ float list_max(const float *sc, int n, int lane) {
     float m = -INFINITY;
-    for (int i = lane; i < n; i += 32) m = fmaxf(m, sc[i]);
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, buf_ld<SH>(sc, i));
     return warp_max(m);
 }
 
 // softmax numerators in place (sc[i] <- e_i = exp_c(s_i - m)) and their canonical sum
 // S = T_0 + T_1 + ... (tile sums by butterfly; 0 + T_0 == T_0 and S + 0 == S exactly, so empty
 // tiles of the unrolled tail are harmless).  UNR tiles are in flight per iteration.
+template <bool SH>
 __device__ __forceinline__ float softmax_exp_sum(float *sc, int n, float m, int lane) {
     float S = 0.0f;
     for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
         float x[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; x[u] = (i < n) ? sc[i] : 0.0f; }
+        for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; x[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             const int i = t0 + 32 * u + lane;
             float e = 0.0f;
-            if (i < n) { e = exp_c(__fsub_rn(x[u], m)); sc[i] = e; }
+            if (i < n) { e = exp_c(__fsub_rn(x[u], m)); buf_st<SH>(sc, i, e); }
             S = __fadd_rn(S, warp_sum_butterfly(e));
         }
     }
@@ -116,56 +138,87 @@ __device__ __forceinline__ float softmax_exp_sum(float *sc, int n, float m, int 
     return S;
 }
 
-// total of the float64 CDF over p_i = e_i / S
-__device__ __forceinline__ double cdf_total(const float *sc, int n, float S, int lane) {
+// total of the float64 CDF over p_i = e_i / S.  Lane (t & 31) also keeps the running total after tile t
+// in car[t >> 5] (tiles 0..63), so that the draw can jump straight to the tile that contains it.
+template <bool SH>
+__device__ __forceinline__ double cdf_total(const float *sc, int n, float S, int lane, double (&car)[2]) {
     double total = 0.0;
+    car[0] = car[1] = 0.0;
     for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
         float e[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? sc[i] : 0.0f; }
+        for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
             double x = (double)__fdiv_rn(e[u], S);   // 0 / S == 0 for the padding lanes
             x = warp_scan_ks(x, lane);
             total = __dadd_rn(total, __shfl_sync(FULL, x, 31));
+            const int t = (t0 >> 5) + u;
+            if (t < 64 && lane == (t & 31)) car[t >> 5] = total;
         }
     }
     return total;
 }
 
-// first i with cdf_i / total > u; all lanes return it
-__device__ __forceinline__ int cdf_pick(const float *sc, int n, float S, double total, double u, int lane) {
-    double carry = 0.0;
-    for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
-        float e[UNR];
-#pragma unroll
-        for (int k = 0; k < UNR; ++k) { const int i = t0 + 32 * k + lane; e[k] = (i < n) ? sc[i] : 0.0f; }
-#pragma unroll
-        for (int k = 0; k < UNR; ++k) {
-            const int i = t0 + 32 * k + lane;
-            double x = (double)__fdiv_rn(e[k], S);
-            x = warp_scan_ks(x, lane);
-            const double q = __ddiv_rn(__dadd_rn(carry, x), total);
-            const unsigned hit = __ballot_sync(FULL, (i < n) && (q > u));
-            if (hit) return t0 + 32 * k + __ffs(hit) - 1;
-            carry = __dadd_rn(carry, __shfl_sync(FULL, x, 31));
-        }
+// first i with cdf_i / total > u, scanning tiles [t_begin, ...) with `carry` = CDF before tile t_begin
+template <bool SH>
+__device__ __forceinline__ int cdf_pick_from(const float *sc, int n, float S, double total, double u, int lane,
+                                             int t_begin, double carry) {
+    for (int t0 = 32 * t_begin; t0 < n; t0 += 32) {
+        const int i = t0 + lane;
+        double x = (double)__fdiv_rn((i < n) ? buf_ld<SH>(sc, i) : 0.0f, S);
+        x = warp_scan_ks(x, lane);
+        const double q = __ddiv_rn(__dadd_rn(carry, x), total);
+        const unsigned hit = __ballot_sync(FULL, (i < n) && (q > u));
+        if (hit) return t0 + __ffs(hit) - 1;
+        carry = __dadd_rn(carry, __shfl_sync(FULL, x, 31));
     }
     return n - 1;
 }
 
+// The CDF is non-decreasing, so the first index with q > u lies in the first tile whose LAST q exceeds u,
+// and that last q is exactly car[t] / total (same operations as the linear scan performs).  All lanes return idx.
+template <bool SH>
+__device__ __forceinline__ int cdf_pick(const float *sc, int n, float S, double total, double u, int lane,
+                                        const double (&car)[2]) {
+    const int ntiles = (n + 31) >> 5;
+    int t_hit = -1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int t = 32 * h + lane;
+        const bool p = (t < ntiles) && (__ddiv_rn(car[h], total) > u);
+        const unsigned mk = __ballot_sync(FULL, p);
+        if (t_hit < 0 && mk) t_hit = 32 * h + __ffs(mk) - 1;
+    }
+    if (t_hit < 0) {   // beyond the 64 tracked tiles (n > 2048): linear scan from tile 64
+        if (ntiles <= 64) return n - 1;
+        const double c63 = __shfl_sync(FULL, car[1], 31);
+        return cdf_pick_from<SH>(sc, n, S, total, u, lane, 64, c63);
+    }
+    double before = 0.0;
+    if (t_hit > 0) {
+        const int tp = t_hit - 1;
+        const double lo = __shfl_sync(FULL, car[0], tp & 31), hi = __shfl_sync(FULL, car[1], tp & 31);
+        before = (tp >> 5) ? hi : lo;
+    }
+    return cdf_pick_from<SH>(sc, n, S, total, u, lane, t_hit, before);
+}
+
 // softmax + CDF + draw over sc[0..n) given its max m (== ggo_choose).  All lanes return the index.
+template <bool SH>
 __device__ __forceinline__ int choose_index(float *sc, int n, float m, double u, int lane) {
-    const float S = softmax_exp_sum(sc, n, m, lane);
-    const double total = cdf_total(sc, n, S, lane);
-    return cdf_pick(sc, n, S, total, u, lane);
+    const float S = softmax_exp_sum<SH>(sc, n, m, lane);
+    double car[2];
+    const double total = cdf_total<SH>(sc, n, S, lane, car);
+    return cdf_pick<SH>(sc, n, S, total, u, lane, car);
 }
 
 // normalised CDF q_i = cdf_i / total written out (the array numpy's choice would searchsorted)
 __device__ __forceinline__ void cdf_store(float *sc, int n, double *q_out, int lane) {
-    const float m = list_max(sc, n, lane);
-    const float S = softmax_exp_sum(sc, n, m, lane);
-    const double total = cdf_total(sc, n, S, lane);
+    const float m = list_max<false>(sc, n, lane);
+    const float S = softmax_exp_sum<false>(sc, n, m, lane);
+    double car[2];
+    const double total = cdf_total<false>(sc, n, S, lane, car);
     double carry = 0.0;
     for (int t0 = 0; t0 < n; t0 += 32) {
         const int i = t0 + lane;

@@ -209,9 +209,8 @@ class GraphGAN(object):
                 train_size = len(center_nodes)
                 start_list = list(range(0, train_size, config.batch_size_dis))
                 self.shuffle_rng.shuffle(start_list)
-                for start in start_list:
-                    end = start + config.batch_size_dis
-                    self.discriminator.d_step(center_nodes[start:end], neighbor_nodes[start:end], labels[start:end])
+                # the per-batch sess.run loop of graph_gan.py:152-157, enqueued from C (identical steps)
+                self.discriminator.train_steps(center_nodes, neighbor_nodes, labels, start_list, config.batch_size_dis)
             # G-steps
             node_1 = node_2 = reward = None
             for g_epoch in range(config.n_epochs_gen):
@@ -220,9 +219,7 @@ class GraphGAN(object):
                 train_size = len(node_1)
                 start_list = list(range(0, train_size, config.batch_size_gen))
                 self.shuffle_rng.shuffle(start_list)
-                for start in start_list:
-                    end = start + config.batch_size_gen
-                    self.generator.g_step(node_1[start:end], node_2[start:end], reward[start:end])
+                self.generator.train_steps(node_1, node_2, reward, start_list, config.batch_size_gen)   # graph_gan.py:171-176
             self.write_embeddings_to_file()
             self.evaluation(self)
         print("training completes")

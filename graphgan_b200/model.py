@@ -98,6 +98,26 @@ class PairModel:
                     "gg_pair_grad")
         self.apply_adam()
 
+    def train_steps(self, node_id, node_neighbor_id, aux, start_list, batch_size):
+        """All optimizer steps of one inner epoch (graph_gan.py:149-157 / 168-176): ``start_list`` is the shuffled
+        list of batch starts; rows come from the device arrays.  Identical to calling ``step`` per batch."""
+        i, j, a = self._dev_i32(node_id), self._dev_i32(node_neighbor_id), self._dev_f32(aux)
+        starts = np.ascontiguousarray(np.asarray(start_list, np.int64))
+        if starts.size == 0:
+            return
+        if batch_size > MAX_BATCH:
+            raise ValueError("batch of %d pairs exceeds GG_MAX_BATCH=%d" % (batch_size, MAX_BATCH))
+        b1p, b2p = C.c_float(float(self.beta1_power)), C.c_float(float(self.beta2_power))
+        _cabi.check(self.lib.gg_train_steps(self._step_mode, int(i.shape[0]), starts.ctypes.data_as(C.c_void_p), int(starts.size),
+                                            int(batch_size), ptr(i), ptr(j), ptr(a), self.n_node, self.ld, ptr(self.emb),
+                                            ptr(self.m_emb), ptr(self.v_emb), ptr(self.bias_t), ptr(self.m_bias), ptr(self.v_bias),
+                                            C.c_float(float(self.lam)), ptr(self.n_unique), ptr(self.uniq_ids), ptr(self.grad_rows),
+                                            ptr(self.grad_bias), ptr(self.row_slot), C.c_float(float(self.lr)),
+                                            C.c_float(float(self.beta1)), C.c_float(float(self.beta2)), C.c_float(float(self.eps)),
+                                            C.byref(b1p), C.byref(b2p), self._stream()), "gg_train_steps")
+        self.beta1_power, self.beta2_power = np.float32(b1p.value), np.float32(b2p.value)
+        self.step_count += int(starts.size)
+
     def apply_adam(self):
         st = self._stream()
         _cabi.check(self.lib.gg_adam_apply(self.n_node, self.ld, ptr(self.emb), ptr(self.m_emb), ptr(self.v_emb),

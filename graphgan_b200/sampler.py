@@ -69,6 +69,13 @@ class WalkPlan:
             self.walk_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
             self.walk_ptr[1:] = torch.cumsum(sample_num.to(torch.int64), 0)      # plumbing: prefix of sample_num
             self.n_walks = int(self.walk_ptr[-1].item())
+        nw = self.walk_ptr[1:] - self.walk_ptr[:-1]
+        self.walk_slot = torch.repeat_interleave(torch.arange(R, dtype=torch.int32, device=dev), nw,
+                                                 output_size=self.n_walks) if self.n_walks else None
+        self.chunk_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+        cw = sampler.chunk_walks
+        self.chunk_ptr[1:] = torch.cumsum((nw + cw - 1) // cw, 0)              # chunks of <= cw walks of one root
+        self.n_chunks = int(self.chunk_ptr[-1].item())
         r = trees.roots.long()
         self.rq_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
         self.rq_ptr[1:] = torch.cumsum(g.indptr[r + 1] - g.indptr[r], 0)       # prefix of the roots' walk degrees
@@ -88,7 +95,7 @@ class WalkPlan:
 
 
 class WalkSampler:
-    def __init__(self, graph, hub_threshold=256):
+    def __init__(self, graph, hub_threshold=256, chunked=False, chunk_walks=8):
         import torch
         self.torch = torch
         self.g = graph
@@ -96,6 +103,8 @@ class WalkSampler:
         self.lib = _cabi.lib()
         self.max_cand = graph.max_deg + 1
         self.hub_threshold = int(hub_threshold)   # 0 disables both per-pass reuses (pure on-demand path)
+        self.chunked = bool(chunked)              # warp per chunk of walks of a root (False: warp per walk)
+        self.chunk_walks = int(chunk_walks)       # walks per chunk (1..32): sharing vs. load balance
         nbytes = C.c_int64(0)
         _cabi.check(self.lib.gg_walk_scratch_bytes(self.max_cand, C.byref(nbytes)), "gg_walk_scratch_bytes")
         self.scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
@@ -139,7 +148,9 @@ class WalkSampler:
                                                                  ptr(plan.wsteps), ptr(plan.wsuml))
         d.paths, d.path_len, d.counters = ptr(plan.paths), ptr(plan.path_len), ptr(plan.counters)
         d.scratch, d.scratch_bytes, d.work_counter = ptr(self.scratch), self.scratch.numel(), ptr(self.work_counter)
-        d.rq_ptr = ptr(plan.rq_ptr)
+        d.rq_ptr, d.walk_slot = ptr(plan.rq_ptr), ptr(plan.walk_slot)
+        if self.chunked and rng_mode == RNG_PHILOX:
+            d.chunk_ptr, d.n_chunks, d.chunk_walks = ptr(plan.chunk_ptr), plan.n_chunks, self.chunk_walks
         if reuse:
             self.g.hub_tiles(self.hub_threshold)
             d.edge_score, d.hub_threshold, d.root_q = ptr(self.g.edge_score), self.hub_threshold, ptr(plan.root_q)

@@ -102,7 +102,13 @@ typedef struct gg_walk_desc {
                                    NULL = compute the root step per walk */
     const int64_t *rq_ptr;      /* device [R+1] offsets into root_q (prefix of the roots' walk-CSR degrees) */
     int32_t hub_threshold;
-    int32_t reserved2;
+    int32_t chunk_walks;        /* walks per chunk, 1..32 (with chunk_ptr) */
+    /* optional chunking (GG_RNG_PHILOX only): one warp advances up to 32 walks of a root together and shares
+       the candidate list of walks standing on the same node.  chunk_ptr: device [R+1] exclusive prefix of
+       ceil(sample_num / chunk_walks); NULL = one warp per walk. */
+    const int64_t *chunk_ptr;
+    int64_t n_chunks;
+    const int32_t *walk_slot;   /* optional device [W]: root slot of every walk (saves a binary search per walk) */
 } gg_walk_desc;
 
 /* all_score[u, v] = e_u.e_v + b_v (generator.py:21) for every walk-CSR entry (u -> v) of the listed hub
@@ -185,6 +191,17 @@ int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_emb, float *v
                   float *m_bias, float *v_bias, const int32_t *n_unique, const int32_t *uniq_ids,
                   const float *grad_rows, const float *grad_bias, int32_t *row_slot, float lr_t,
                   float beta1, float beta2, float eps, void *stream);
+
+/* The inner training loop of graph_gan.py:149-157 / 168-176: for each start in start_list (host array, already
+ * shuffled by the caller): one optimizer step on rows [start, min(start + batch_size, n_rows)) of the device
+ * arrays node_id / node_neighbor_id / aux -- i.e. gg_pair_grad + gg_adam_apply per step, enqueued from C so that
+ * the per-step cost is two kernel launches, not a round trip through the host language.  beta1_power/beta2_power:
+ * host in/out, the AdamOptimizer's beta^t accumulators (fp32, multiplied once per step like TF's _finish). */
+int gg_train_steps(int32_t mode, int64_t n_rows, const int64_t *start_list, int64_t n_starts, int32_t batch_size,
+                   const int32_t *node_id, const int32_t *node_neighbor_id, const float *aux, int64_t n_node, int32_t ld,
+                   float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias, float *v_bias, float lambda,
+                   int32_t *n_unique, int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot, float lr,
+                   float beta1, float beta2, float eps, float *beta1_power, float *beta2_power, void *stream);
 
 /* get_node_pairs_from_path (graph_gan.py:272-291) for a batch of recorded paths.
  * pair_ptr: device [W+1] (out, exclusive scan of per-path pair counts). */

@@ -225,3 +225,25 @@ def test_trainer_epoch_on_cagrqc(cuda_device, tmp_path, monkeypatch):
     assert gan.get_node_pairs_from_path([1, 0, 2, 4, 2]) == [[1, 0], [1, 2], [0, 1], [0, 2], [0, 4], [2, 1], [2, 0], [2, 4], [4, 0], [4, 2]]
     s, p = gan.sample(0, None, 3, for_d=False)
     assert s is None or (len(s) == 3 and all(q[-1] == q[-3] for q in p))
+
+
+def test_train_steps_equals_step_by_step(cuda_device):
+    """gg_train_steps (the C-driven batch loop) == calling d_step / g_step per batch, bit for bit, including the
+    short last batch and the beta-power bookkeeping."""
+    import torch
+    from graphgan_b200.discriminator import Discriminator
+    from graphgan_b200.generator import Generator
+    rs = np.random.RandomState(21)
+    n, d, M, B = 700, 50, 1000, 64
+    emb = rs.normal(0, 0.5, size=(n, d))
+    i, j = rs.randint(0, n, M).astype(np.int32), rs.randint(0, n, M).astype(np.int32)
+    starts = list(range(0, M, B))
+    rs.shuffle(starts)
+    for cls, aux in ((Discriminator, (rs.random_sample(M) < 0.5).astype(np.float32)), (Generator, (rs.random_sample(M) * 3).astype(np.float32))):
+        a, b = cls(n, emb, device=cuda_device), cls(n, emb, device=cuda_device)
+        for s0 in starts:
+            a.step(i[s0:s0 + B], j[s0:s0 + B], aux[s0:s0 + B])
+        b.train_steps(i, j, aux, starts, B)
+        assert torch.equal(a.emb, b.emb) and torch.equal(a.bias_t, b.bias_t) and torch.equal(a.v_emb, b.v_emb)
+        assert a.beta1_power == b.beta1_power and a.beta2_power == b.beta2_power and a.step_count == b.step_count
+        assert float(a.lr_t()) == float(b.lr_t())

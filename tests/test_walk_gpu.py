@@ -11,7 +11,7 @@ from tests.golden import loader
 pytestmark = pytest.mark.gpu
 
 
-def _setup(case, cuda_device, roots=None, hub_threshold=256):
+def _setup(case, cuda_device, roots=None, hub_threshold=256, chunked=True, chunk_walks=32):
     import torch
     from graphgan_b200 import graph as G, sampler as S
     from oracle import canonical as can
@@ -24,7 +24,7 @@ def _setup(case, cuda_device, roots=None, hub_threshold=256):
     indptr, adj = can.unique_csr(case.graph)
     assert np.array_equal(hg.indptr, indptr) and np.array_equal(hg.adj, adj)
     dg = G.DeviceGraph(hg, cuda_device)
-    smp = S.WalkSampler(dg, hub_threshold=hub_threshold)
+    smp = S.WalkSampler(dg, hub_threshold=hub_threshold, chunked=chunked, chunk_walks=chunk_walks)
     roots = np.arange(case.n, dtype=np.int32) if roots is None else np.asarray(roots, np.int32)
     trees = smp.build_trees(roots)
     emb = S.pad_embedding(case.emb_g, cuda_device)
@@ -95,11 +95,11 @@ def test_stream_replay_matches_reference(name, hub, cuda_device):
         assert got[k] == pf[pp[k]:pp[k + 1]].tolist()
 
 
-def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256):
+def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256, chunked=True, chunk_walks=32):
     import torch
     from graphgan_b200 import sampler as S
     from oracle import canonical as can
-    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold)
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold, chunked, chunk_walks)
     par = trees.parent.cpu().numpy()
     E = can.pad_rows(case.emb_g)
     bits = np.zeros(dg.n_bit_words, np.uint32)
@@ -148,6 +148,14 @@ def test_philox_matches_canonical_oracle(name, ratio, hub, cuda_device):
                     hub_threshold=hub)
 
 
+@pytest.mark.parametrize("name,hub,ratio", [("rand300", 0, 0.6), ("rand1200", 256, 1.0), ("cagrqc", 8, 1.0)])
+def test_philox_warp_per_walk_kernel(name, hub, ratio, cuda_device):
+    """The un-chunked order-free kernel (one warp per walk) stays available (chunk_ptr = NULL) and agrees too."""
+    case = loader.load(name)
+    _philox_compare(case, cuda_device, None, ratio, seed=4242, n_sample_gen=int(case.n_sample_gen), hub_threshold=hub,
+                    chunked=False)
+
+
 @pytest.mark.parametrize("hub", [0, 64, 256])
 def test_hub_lists_use_global_scratch(hub, cuda_device):
     """A power-law graph whose hub has > SMEM_CAP neighbours: the long-list (global scratch) path
@@ -163,7 +171,70 @@ def test_hub_lists_use_global_scratch(hub, cuda_device):
     case["graph"] = [hg.neighbors(i).tolist() for i in range(n)]
     rs = np.random.RandomState(0)
     roots = np.sort(rs.choice(np.flatnonzero(hg.degrees() > 0), 400, replace=False))
-    cnt, cg = _philox_compare(case, cuda_device, roots, 1.0, seed=99, n_sample_gen=6, hub_threshold=hub)
+    cnt, cg = _philox_compare(case, cuda_device, roots, 1.0, seed=99, n_sample_gen=6, hub_threshold=hub,
+                              chunk_walks={0: 32, 64: 8, 256: 5}[hub])
     assert cnt["steps"] > 0
     if hub:   # the reuse must actually remove row gathers
         assert cnt["rows_gathered"] < cnt["raw_sum_l"]
+
+
+@pytest.mark.parametrize("hub", [0, 256])
+def test_giant_hub_lists_beyond_the_smem_score_buffer(hub, cuda_device):
+    """A 3000+-neighbour hub: candidate lists longer than the 2048-score shared buffer and than the 64 tiles
+    whose running totals the draw tracks (global-scratch scores, linear tail scan), at ld = 32 (CPL = 1)."""
+    import torch
+    from graphgan_b200 import graph as G, sampler as S, synth
+    from oracle import canonical as can
+    n, d = 3600, 32
+    rs = np.random.RandomState(8)
+    star = np.stack([np.zeros(n - 1, np.int64), rs.permutation(np.arange(1, n))], 1)
+    extra = synth.power_law(n, 6, seed=9)
+    edges = np.concatenate([star[:1500], extra, star[1500:]])
+    hg = G.HostGraph(edges, None, n_node=n)
+    assert hg.max_deg >= n - 1
+    emb_h = synth.embeddings(n, d, seed=10, sigma=0.4)
+    dg = G.DeviceGraph(hg, cuda_device)
+    smp = S.WalkSampler(dg, hub_threshold=hub)
+    roots = np.asarray([0, 3, 11, 200, 1999, 3599], np.int32)
+    trees = smp.build_trees(roots)
+    par = trees.parent.cpu().numpy()
+    assert np.array_equal(par, can.bfs_parents(hg.indptr, hg.adj, roots))
+    emb = S.pad_embedding(emb_h, cuda_device)
+    bias_h = rs.normal(0, 0.2, n).astype(np.float32)
+    bias = torch.as_tensor(bias_h).to(cuda_device)
+    sample_num = np.asarray([120, 40, 40, 40, 40, 40], np.int64)
+    bits = np.zeros(dg.n_bit_words, np.uint32)
+    E = can.pad_rows(emb_h)
+    for for_d, tag in ((True, 1), (False, 2)):
+        ref = can.walk_pass(E, bias_h, hg.indptr, hg.adj, roots, par, sample_num, for_d, bits, seed=5, pass_tag=tag, max_path=16)
+        out = smp.run(emb, bias, trees, torch.as_tensor(sample_num).to(cuda_device), for_d, seed=5, pass_tag=tag, max_path=16)
+        assert ref.max_l > 2100
+        assert np.array_equal(out.status.cpu().numpy(), ref.status)
+        assert np.array_equal(out.samples.cpu().numpy(), ref.samples)
+        assert np.array_equal(out.wsuml.cpu().numpy(), ref.wsuml)
+        assert np.array_equal(dg.d1_bits.cpu().numpy().view(np.uint32), bits)
+
+
+def test_partition_invariance(cuda_device):
+    """Philox is keyed by (root, walk, step): the rows of a root do not depend on which other roots share its
+    batch (or its GPU).  Two half batches == one full batch, row for row."""
+    import torch
+    from graphgan_b200 import sampler as S
+    case = loader.load("rand1200")
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device)
+    full = smp.run(emb, bias, trees, dg.raw_deg, True, seed=77, pass_tag=9)
+    fc, fn, fl, fk = (x.clone() for x in smp.emit_d_rows(full))
+    fk = int(fk.item())
+    bits_full = dg.d1_bits.clone()
+    dg.reset_tree_mutations()
+    parts = []
+    for lo, hi in ((0, 500), (500, 1200)):
+        t = S.TreeBatch(trees.roots[lo:hi].contiguous(), trees.parent[lo:hi].contiguous())
+        o = smp.run(emb, bias, t, dg.raw_deg[lo:hi].contiguous(), True, seed=77, pass_tag=9)
+        c, nb, lb, k = smp.emit_d_rows(o)
+        k = int(k.item())
+        parts.append((c[:k].clone(), nb[:k].clone(), lb[:k].clone()))
+    assert torch.equal(torch.cat([p[0] for p in parts]), fc[:fk])
+    assert torch.equal(torch.cat([p[1] for p in parts]), fn[:fk])
+    assert torch.equal(torch.cat([p[2] for p in parts]), fl[:fk])
+    assert torch.equal(dg.d1_bits, bits_full)
