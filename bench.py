@@ -46,7 +46,8 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--hub-threshold", type=int, default=256, help="degree from which adjacency scores are cached per pass")
-    p.add_argument("--chunk-walks", type=int, default=0, help="walks of a root advanced together by one warp (0: warp per walk)")
+    p.add_argument("--algo", default="walk", choices=["chunk", "walk"], help="order-free walk kernel")
+    p.add_argument("--chunk-walks", type=int, default=8, help="walks per chunk for --algo chunk")
     return p.parse_args()
 
 
@@ -279,7 +280,7 @@ def run_b200(args):
 
     hg, emb_h, roots, d = make_inputs(args, rank)
     dg = G.DeviceGraph(hg, dev)
-    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, chunked=args.chunk_walks > 0, chunk_walks=max(args.chunk_walks, 1))
+    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, algo=args.algo, chunk_walks=args.chunk_walks)
     emb = S.pad_embedding(emb_h, dev)
     bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
     t0 = time.time()

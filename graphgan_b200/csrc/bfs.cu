@@ -16,7 +16,8 @@
 //
 // One 1024-thread CTA owns one root at a time.  Per level: (A) prefix sums over the frontier,
 // (B) claim sweep, (C) winner sweep (records one win bit per frontier edge), (D) prefix sum of
-// the winner counts, (E) scatter from the win bits.  A visited bitmap in SHARED memory (N bits;
+// the winner counts, (E) scatter from the win bits.  Small frontier nodes (degree <= 32) are
+// processed one per thread, large ones one per warp.  A visited bitmap in SHARED memory (N bits;
 // global scratch when N > ~1.7M) filters already-discovered heads, so the only random global
 // accesses are one atomicMin + one 4-byte read per edge into the NEXT level.
 // HBM/L2-bound integer work; no tensor cores.
@@ -31,7 +32,7 @@ constexpr long long BFS_SMEM_BITMAP_MAX_BYTES = 200 * 1024;
 
 __host__ __device__ inline long long bfs_words_per_cta(long long n, long long nnz, bool bitmap_in_smem) {
     const long long bm = bitmap_in_smem ? 0 : (n + 31) / 32;
-    return 7 * n + nnz / 32 + bm + 8;
+    return 8 * n + nnz / 32 + bm + 8;
 }
 
 // exclusive scan of f(i), i in [0,n), into out[0..n]; returns total (block-wide, all threads).
@@ -79,7 +80,7 @@ bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr
            int bitmap_in_smem) {
     extern __shared__ unsigned s_bitmap[];
     __shared__ unsigned s_warp[32];
-    __shared__ unsigned s_carry;
+    __shared__ unsigned s_carry, s_nbig;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t N = (size_t)n_node;
     const size_t bm_words = (N + 31) / 32;
@@ -90,7 +91,8 @@ bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr
     unsigned *base = off + N + 1;                            // [N+1] winners per frontier node / compaction offsets
     unsigned *woff = base + N + 1;                           // [N+1] first win-mask word of a frontier node
     unsigned *wmask = woff + N + 1;                          // [nnz/32 + N + 1]
-    unsigned *bm = bitmap_in_smem ? s_bitmap : (wmask + nnz / 32 + N + 1);
+    unsigned *big = wmask + nnz / 32 + N + 1;                // [N] frontier indices of nodes with degree > 32
+    unsigned *bm = bitmap_in_smem ? s_bitmap : (big + N);
 
     for (long long r = blockIdx.x; r < n_roots; r += gridDim.x) {
         const int root = roots[r];
@@ -110,8 +112,27 @@ bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr
             block_exclusive_scan(
                 [&](unsigned i) { const int u = cur[i]; return (unsigned)((indptr[u + 1] - indptr[u] + 31) >> 5); }, woff, nf,
                 s_warp, &s_carry);
+            // Work assignment (per sweep): a frontier node of degree <= 32 is handled by ONE THREAD (32 nodes
+            // per warp advance in parallel -- most nodes of a power-law graph are small, and a warp per node would
+            // spend its time on the dependent cur -> indptr -> adj latency chain); larger nodes are collected in
+            // `big` during sweep B and handled by a whole warp, 128 edges in flight.
+            if (threadIdx.x == 0) s_nbig = 0;
+            __syncthreads();
             // B: every frontier edge with an undiscovered head claims it with its visit order
-            for (unsigned i = wid; i < nf; i += BFS_WARPS) {
+            for (unsigned i = threadIdx.x; i < nf; i += BFS_THREADS) {
+                const int u = cur[i];
+                const long long a0 = indptr[u];
+                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
+                if (dg > 32) { big[atomicAdd(&s_nbig, 1u)] = i; continue; }
+                for (unsigned j = 0; j < dg; ++j) {
+                    const int v = __ldg(adj + a0 + j);
+                    if (!((bm[v >> 5] >> (v & 31)) & 1u)) atomicMin(claim + v, q0 + j);
+                }
+            }
+            __syncthreads();
+            const unsigned nbig = s_nbig;
+            for (unsigned b = wid; b < nbig; b += BFS_WARPS) {
+                const unsigned i = big[b];
                 const int u = cur[i];
                 const long long a0 = indptr[u];
                 const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
@@ -126,7 +147,21 @@ bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr
             }
             __syncthreads();
             // C: winners per frontier node, one win bit per edge
-            for (unsigned i = wid; i < nf; i += BFS_WARPS) {
+            for (unsigned i = threadIdx.x; i < nf; i += BFS_THREADS) {
+                const int u = cur[i];
+                const long long a0 = indptr[u];
+                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
+                if (dg > 32) continue;
+                unsigned mk = 0;
+                for (unsigned j = 0; j < dg; ++j) {
+                    const int v = __ldg(adj + a0 + j);
+                    if (!((bm[v >> 5] >> (v & 31)) & 1u) && __ldcg(claim + v) == q0 + j) mk |= 1u << j;
+                }
+                if (dg) wmask[woff[i]] = mk;
+                base[i] = __popc(mk);
+            }
+            for (unsigned b = wid; b < nbig; b += BFS_WARPS) {
+                const unsigned i = big[b];
                 const int u = cur[i];
                 const long long a0 = indptr[u];
                 const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i], w0 = woff[i];
@@ -156,12 +191,30 @@ bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr
             // D: stable compaction offsets
             const unsigned n_next = block_exclusive_scan([&](unsigned i) { return base[i]; }, base, nf, s_warp, &s_carry);
             // E: winners become children (father = u) and the next frontier, in q order
-            for (unsigned i = wid; i < nf; i += BFS_WARPS) {
+            for (unsigned i = threadIdx.x; i < nf; i += BFS_THREADS) {
+                unsigned o = base[i];
+                if (base[i + 1] == o) continue;   // no winner under this node
+                const int u = cur[i];
+                const long long a0 = indptr[u];
+                const unsigned dg = (unsigned)(indptr[u + 1] - a0);
+                if (dg > 32) continue;
+                unsigned mk = wmask[woff[i]];
+                while (mk) {
+                    const int j = __ffs(mk) - 1;
+                    mk &= mk - 1u;
+                    const int v = __ldg(adj + a0 + j);
+                    nxt[o++] = v;
+                    par[v] = u;
+                    atomicOr(bm + (v >> 5), 1u << (v & 31));
+                }
+            }
+            for (unsigned b = wid; b < nbig; b += BFS_WARPS) {
+                const unsigned i = big[b];
+                unsigned o = base[i];
+                if (base[i + 1] == o) continue;
                 const int u = cur[i];
                 const long long a0 = indptr[u];
                 const unsigned dg = (unsigned)(indptr[u + 1] - a0), w0 = woff[i];
-                unsigned o = base[i];
-                if (base[i + 1] == o) continue;   // no winner under this node
                 for (unsigned j0 = 0; j0 < dg; j0 += 32) {
                     const unsigned mk = wmask[w0 + (j0 >> 5)];
                     if (mk == 0u) continue;

@@ -88,7 +88,9 @@ extern "C" int gg_hub_scores(int64_t n_tiles, const int32_t *tile_node, const in
 }
 
 extern "C" int gg_root_cdf(const gg_walk_desc *dp, float *root_sc, double *root_q, void *stream) {
-    GG_REQUIRE(dp && root_sc && root_q, "null pointer");
+    GG_REQUIRE(dp, "null descriptor");
+    if (dp->n_roots == 0) return 0;
+    GG_REQUIRE(root_sc && root_q, "null pointer");
     const gg_walk_desc &d = *dp;
     GG_REQUIRE(d.roots && d.indptr && d.adj && d.emb && d.bias && d.rq_ptr, "null pointer in descriptor");
     GG_REQUIRE(d.ld > 0 && d.ld % 32 == 0, "ld must be a positive multiple of 32");

@@ -70,14 +70,7 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t 
             if (isc) {
                 const int pos = n + __popc(mk & lt);
                 ids[pos] = v[k];
-                if (cached) {
-                    sc[pos] = cs[k]; m = fmaxf(m, cs[k]);
-                } else {
-                    // the row will be scored on demand in a moment: start its DRAM fetch now, for all
-                    // candidates at once (the scoring loop itself only keeps 8 rows in flight per warp)
-                    const float *row = d.emb + (size_t)v[k] * (size_t)d.ld;
-                    for (int b = 0; b < d.ld; b += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
-                }
+                if (cached) { sc[pos] = cs[k]; m = fmaxf(m, cs[k]); }
             }
             n += __popc(mk);
         }
@@ -97,7 +90,7 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t 
         m = warp_max(m);
         if (inc_father) m = fmaxf(m, sc[0]);
     } else {
-        m = (sc == s_sc) ? list_max<true>(sc, n, lane) : list_max<false>(sc, n, lane);
+        m = list_max<false>(sc, n, lane);
     }
     m_out = m;
     cyc[1] += (unsigned int)(clock64() - t_s);
@@ -147,7 +140,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             const long long t_c = clock64();
             const double u = rng.draw((uint32_t)root, k, (uint32_t)step);
             if (rng.exhausted) { status = GG_NOTRUN; break; }
-            idx = (sc == s_sc) ? choose_index<true>(sc, n, m, u, lane) : choose_index<false>(sc, n, m, u, lane);
+            idx = choose_index<false>(sc, n, m, u, lane);
             nxt = ids[idx];
             __syncwarp();
             cyc[2] += (unsigned int)(clock64() - t_c);
@@ -327,18 +320,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_chunk_kernel(const
                 if ((grp >> lane) & 1u) status = GG_VOID;
             } else {
                 const long long t_c = clock64();
-                const bool sh = (sc == s_sc);
-                const float S = sh ? softmax_exp_sum<true>(sc, n, m, lane) : softmax_exp_sum<false>(sc, n, m, lane);
+                const float S = softmax_exp_sum<false>(sc, n, m, lane);
                 double car[2];
-                const double total = sh ? cdf_total<true>(sc, n, S, lane, car) : cdf_total<false>(sc, n, S, lane, car);
+                const double total = cdf_total<false>(sc, n, S, lane, car);
                 const long long a0c = d.indptr[ccur];
                 for (unsigned rest = grp; rest; rest &= rest - 1u) {
                     const int j = __ffs(rest) - 1;
                     const uint32_t kj = __shfl_sync(FULL, k, j);
                     uint32_t a, b;
                     philox4x32_10((uint32_t)root, kj, (uint32_t)cstep, d.pass_tag, k0key, k1key, a, b);
-                    const int idx = sh ? cdf_pick<true>(sc, n, S, total, u53(a, b), lane, car)
-                                       : cdf_pick<false>(sc, n, S, total, u53(a, b), lane, car);
+                    const int idx = cdf_pick<false>(sc, n, S, total, u53(a, b), lane, car);
                     const int nxt = ids[idx];
                     if (lane == j) {
                         if (cstep == 0) fedge = (int)(a0c + idx);
@@ -506,6 +497,7 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
     GG_REQUIRE(dp, "null descriptor");
     const gg_walk_desc &d = *dp;
     GG_REQUIRE(d.ld > 0 && d.ld % 32 == 0, "ld must be a positive multiple of 32");
+    if (d.n_walks == 0 || d.n_roots == 0) return 0;   // nothing to do (empty batches carry null pointers)
     GG_REQUIRE(d.emb && d.bias && d.indptr && d.adj && d.roots && d.parent && d.walk_ptr, "null graph/embedding pointer");
     GG_REQUIRE(d.samples && d.status && d.first_edge && d.wsteps && d.wsuml && d.counters && d.work_counter,
                "null output pointer");
@@ -589,7 +581,8 @@ extern "C" int gg_emit_d_rows(int64_t n_roots, const int32_t *roots, const int64
                               const int64_t *pos_indptr, const int32_t *pos_flat, const int32_t *root_ok,
                               const int32_t *samples, int64_t *row_ptr, int32_t *center, int32_t *neighbor,
                               int32_t *label, int64_t *n_rows_out, void *stream) {
-    GG_REQUIRE(roots && walk_ptr && pos_indptr && pos_flat && root_ok && samples && row_ptr && n_rows_out, "null pointer");
+    GG_REQUIRE(row_ptr && n_rows_out, "null pointer");
+    GG_REQUIRE(n_roots == 0 || (roots && walk_ptr && pos_indptr && pos_flat && root_ok && samples), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 256;
     if (n_roots > 0) {

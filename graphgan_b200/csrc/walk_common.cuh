@@ -88,25 +88,11 @@ __device__ __forceinline__ void score_edges(const float *__restrict__ emb, const
     __syncwarp();
 }
 
-// The score buffer is either this warp's shared-memory slice or its global scratch.  Going through a generic
-// pointer makes every access a generic LD/ST (long-scoreboard latency even when it lands in shared memory), so
-// the passes below are instantiated for both address spaces and use LDS/STS on the shared path.
-template <bool SH> __device__ __forceinline__ float buf_ld(const float *p, int i) {
-    if constexpr (SH) {
-        float v;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p + i)));
-        return v;
-    } else {
-        return p[i];
-    }
-}
-template <bool SH> __device__ __forceinline__ void buf_st(float *p, int i, float v) {
-    if constexpr (SH) {
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p + i)), "f"(v));
-    } else {
-        p[i] = v;
-    }
-}
+// The score buffer is either this warp's shared-memory slice or its global scratch (generic pointer).  An
+// LDS/STS specialisation of the shared path was measured (round 1) and was not faster than generic LD/ST, so
+// the SH template parameter is kept only as a hook.
+template <bool SH> __device__ __forceinline__ float buf_ld(const float *p, int i) { return p[i]; }
+template <bool SH> __device__ __forceinline__ void buf_st(float *p, int i, float v) { p[i] = v; }
 
 // max over sc[0..n)
 template <bool SH>

@@ -63,8 +63,10 @@ class GraphGAN(object):
         self.lib = _cabi.lib()
 
         # BFS trees: resident for all roots when they fit (the reference's pickle cache, graph_gan.py:31-46)
-        self.trees = None
-        if 4 * self.n_node * self.n_node <= config.tree_cache_bytes:
+        self.trees, self._tree_key = None, None
+        import torch.distributed as _d
+        if not (_d.is_available() and _d.is_initialized() and _d.get_world_size() > 1) and \
+                4 * self.n_node * self.n_node <= config.tree_cache_bytes:
             print("constructing BFS-trees...")
             self.trees = self.construct_trees(self.root_nodes)
 
@@ -77,6 +79,14 @@ class GraphGAN(object):
         self.shuffle_rng = np.random.RandomState(config.seed)
         self.pass_counter = 0
         self.last_counters = {}
+        # one process per GPU: roots are sharded, rows all-gathered, updates data parallel (parallel.py)
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.world = self.dist.get_world_size() if self.dist else 1
+        if self.dist:
+            from .parallel import DataParallelStep
+            self._dp_d, self._dp_g = DataParallelStep(self.discriminator), DataParallelStep(self.generator)
 
     # ------------------------------------------------------------------ trees (graph_gan.py:63-108)
     def construct_trees(self, nodes):
@@ -96,6 +106,17 @@ class GraphGAN(object):
     # ------------------------------------------------------------------ root batching
     def _root_batches(self, roots):
         roots = np.asarray(roots, np.int32)
+        if self.dist:   # this rank's contiguous, degree-balanced block of the root list (same for D and G passes)
+            from .parallel import balanced_root_ranges
+            lo, hi = balanced_root_ranges(self.host_graph.degrees()[roots] + 1, self.world)[self.rank]
+            roots = roots[lo:hi]
+            if self.trees is not None and self._tree_key != (lo, hi):
+                self.trees = None
+            if self.trees is None and 4 * self.n_node * max(hi - lo, 1) <= config.tree_cache_bytes:
+                self.trees, self._tree_key = self.construct_trees(roots), (lo, hi)
+            if self.trees is not None:
+                yield self.trees
+                return
         if self.trees is not None and roots.shape[0] == self.n_node and np.array_equal(roots, np.arange(self.n_node)):
             yield self.trees
             return
@@ -126,7 +147,11 @@ class GraphGAN(object):
                 tot[key] += cnt[key]
         self.last_counters = tot
         cat = lambda xs, dt: torch.cat(xs) if xs else torch.zeros(0, dtype=dt, device=self.device)
-        return cat(cs, torch.int32), cat(ns, torch.int32), cat(ls, torch.int32).float()
+        c, n, l = cat(cs, torch.int32), cat(ns, torch.int32), cat(ls, torch.int32)
+        if self.dist:   # every rank ends up with the full row lists, in root order
+            from .parallel import all_gather_varlen
+            c, n, l = all_gather_varlen(c), all_gather_varlen(n), all_gather_varlen(l)
+        return c, n, l.float()
 
     # ------------------------------------------------------------------ graph_gan.py:204-223
     def prepare_data_for_g(self, roots=None):
@@ -155,6 +180,9 @@ class GraphGAN(object):
             n1s.append(n1[:m]); n2s.append(n2[:m])
         node_1 = torch.cat(n1s) if n1s else torch.zeros(0, dtype=torch.int32, device=self.device)
         node_2 = torch.cat(n2s) if n2s else torch.zeros(0, dtype=torch.int32, device=self.device)
+        if self.dist:
+            from .parallel import all_gather_varlen
+            node_1, node_2 = all_gather_varlen(node_1), all_gather_varlen(node_2)
         reward = self.discriminator.reward_pairs(node_1, node_2)     # graph_gan.py:220-222, one fetch for all pairs
         return node_1, node_2, reward
 
@@ -210,7 +238,12 @@ class GraphGAN(object):
                 start_list = list(range(0, train_size, config.batch_size_dis))
                 self.shuffle_rng.shuffle(start_list)
                 # the per-batch sess.run loop of graph_gan.py:152-157, enqueued from C (identical steps)
-                self.discriminator.train_steps(center_nodes, neighbor_nodes, labels, start_list, config.batch_size_dis)
+                if self.dist:
+                    for start in start_list:
+                        end = start + config.batch_size_dis
+                        self._dp_d.step(center_nodes[start:end], neighbor_nodes[start:end], labels[start:end])
+                else:
+                    self.discriminator.train_steps(center_nodes, neighbor_nodes, labels, start_list, config.batch_size_dis)
             # G-steps
             node_1 = node_2 = reward = None
             for g_epoch in range(config.n_epochs_gen):
@@ -219,13 +252,20 @@ class GraphGAN(object):
                 train_size = len(node_1)
                 start_list = list(range(0, train_size, config.batch_size_gen))
                 self.shuffle_rng.shuffle(start_list)
-                self.generator.train_steps(node_1, node_2, reward, start_list, config.batch_size_gen)   # graph_gan.py:171-176
+                if self.dist:
+                    for start in start_list:
+                        end = start + config.batch_size_gen
+                        self._dp_g.step(node_1[start:end], node_2[start:end], reward[start:end])
+                else:
+                    self.generator.train_steps(node_1, node_2, reward, start_list, config.batch_size_gen)   # graph_gan.py:171-176
             self.write_embeddings_to_file()
             self.evaluation(self)
         print("training completes")
 
     # ------------------------------------------------------------------ graph_gan.py:293-319
     def write_embeddings_to_file(self):
+        if self.rank != 0:      # replicas are bit-identical; one writer
+            return
         modes = [self.generator, self.discriminator]
         for i in range(2):
             os.makedirs(os.path.dirname(config.emb_filenames[i]) or ".", exist_ok=True)
@@ -234,6 +274,8 @@ class GraphGAN(object):
     @staticmethod
     def evaluation(self):
         results = []
+        if getattr(self, "rank", 0) != 0:
+            return results
         if config.app == "link_prediction":
             for i in range(2):
                 lpe = lp.LinkPredictEval(config.emb_filenames[i], config.test_filename, config.test_neg_filename,

@@ -23,12 +23,16 @@ def round_up(x, m):
 
 
 def pad_embedding(emb, device=None):
-    """float64/32 [N, d] -> fp32 [N, ld] device tensor, ld = round_up(d, 32), zero padded
+    """float64/32 [N, d] -> fp32 [N, ld] device tensor, ld = 32 * 2^k >= d (32, 64, 128 or 256), zero padded
     (the tf fp32 variable of generator.py:11-14 in the HBM layout of DESIGN.md section 2)."""
     import torch
     e = emb.float() if isinstance(emb, torch.Tensor) else torch.as_tensor(np.asarray(emb, np.float64).astype(np.float32))
     n, d = e.shape
-    ld = round_up(d, 32)
+    if d > 256:
+        raise ValueError("n_emb = %d is not supported (the kernels are instantiated for row strides 32, 64, 128, 256)" % d)
+    ld = 32
+    while ld < d:      # zero columns add exactly +0 to every canonical dot, so the amount of padding is invisible
+        ld *= 2
     out = torch.zeros((n, ld), dtype=torch.float32, device=device if device is not None else e.device)
     out[:, :d] = e.to(out.device)
     return out
@@ -95,7 +99,7 @@ class WalkPlan:
 
 
 class WalkSampler:
-    def __init__(self, graph, hub_threshold=256, chunked=False, chunk_walks=8):
+    def __init__(self, graph, hub_threshold=256, algo="walk", chunk_walks=8):
         import torch
         self.torch = torch
         self.g = graph
@@ -103,8 +107,11 @@ class WalkSampler:
         self.lib = _cabi.lib()
         self.max_cand = graph.max_deg + 1
         self.hub_threshold = int(hub_threshold)   # 0 disables both per-pass reuses (pure on-demand path)
-        self.chunked = bool(chunked)              # warp per chunk of walks of a root (False: warp per walk)
-        self.chunk_walks = int(chunk_walks)       # walks per chunk (1..32): sharing vs. load balance
+        # order-free (Philox) kernel: "walk" = one warp per walk (default, fastest measured); "chunk" = one warp
+        # advances chunk_walks walks of a root together and shares the candidate list of walks on the same node
+        assert algo in ("chunk", "walk")
+        self.algo = algo
+        self.chunk_walks = int(chunk_walks)
         nbytes = C.c_int64(0)
         _cabi.check(self.lib.gg_walk_scratch_bytes(self.max_cand, C.byref(nbytes)), "gg_walk_scratch_bytes")
         self.scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
@@ -149,7 +156,7 @@ class WalkSampler:
         d.paths, d.path_len, d.counters = ptr(plan.paths), ptr(plan.path_len), ptr(plan.counters)
         d.scratch, d.scratch_bytes, d.work_counter = ptr(self.scratch), self.scratch.numel(), ptr(self.work_counter)
         d.rq_ptr, d.walk_slot = ptr(plan.rq_ptr), ptr(plan.walk_slot)
-        if self.chunked and rng_mode == RNG_PHILOX:
+        if self.algo == "chunk" and rng_mode == RNG_PHILOX:
             d.chunk_ptr, d.n_chunks, d.chunk_walks = ptr(plan.chunk_ptr), plan.n_chunks, self.chunk_walks
         if reuse:
             self.g.hub_tiles(self.hub_threshold)

@@ -93,6 +93,38 @@ def main(mode):
         rows = [torch.empty_like(repl.emb) for _ in range(world)]
         dist.all_gather(rows, repl.emb)
         assert all(torch.equal(rows[0], r) for r in rows[1:])
+    # (3) the re-hosted trainer under torch.distributed: sharded sampling + data-parallel updates
+    from graphgan_b200 import config
+    from graphgan_b200.graph_gan import GraphGAN
+    from tests.golden import loader
+    import tempfile
+    c = loader.load("rand1200")
+    tmp = tempfile.mkdtemp()
+    config.n_emb, config.n_epochs, config.n_epochs_dis, config.dis_interval = 50, 1, 1, 1
+    config.n_epochs_gen, config.gen_interval, config.n_sample_gen, config.seed = 1, 1, 2, 9
+    config.app = "none"
+    config.emb_filenames = [os.path.join(tmp, "g%d.emb" % rank), os.path.join(tmp, "d%d.emb" % rank)]
+    config.result_filename, config.model_log = os.path.join(tmp, "r%d.txt" % rank), tmp + "/"
+    hgc = G.HostGraph(c.train_edges, c.test_edges)
+    gan = GraphGAN(host_graph=hgc, node_embed_init_d=c.emb_d, node_embed_init_g=c.emb_g)
+    assert gan.world == world
+    ce, ne, la = gan.prepare_data_for_d()
+    if rank == 0:   # the same pass on one GPU (no process group in this instance)
+        solo = GraphGAN.__new__(GraphGAN)
+        solo.__dict__.update(gan.__dict__)
+        solo.dist, solo.rank, solo.world, solo.trees, solo._tree_key = None, 0, 1, None, None
+        solo.pass_counter = gan.pass_counter - 1
+        solo.device_graph.reset_tree_mutations()
+        se, sn, sl = solo.prepare_data_for_d()
+        assert torch.equal(se, ce) and torch.equal(sn, ne) and torch.equal(sl, la)
+    dist.barrier()
+    gan.device_graph.reset_tree_mutations()
+    gan.pass_counter = 0
+    gan.trees, gan._tree_key = None, None
+    gan.train()
+    rows = [torch.empty_like(gan.generator.emb) for _ in range(world)]
+    dist.all_gather(rows, gan.generator.emb)
+    assert all(torch.equal(rows[0], r) for r in rows[1:])
     dist.barrier()
     if rank == 0:
         print("DIST_GPU_OK")

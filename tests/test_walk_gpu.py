@@ -11,7 +11,7 @@ from tests.golden import loader
 pytestmark = pytest.mark.gpu
 
 
-def _setup(case, cuda_device, roots=None, hub_threshold=256, chunked=True, chunk_walks=32):
+def _setup(case, cuda_device, roots=None, hub_threshold=256, algo="chunk", chunk_walks=32):
     import torch
     from graphgan_b200 import graph as G, sampler as S
     from oracle import canonical as can
@@ -24,7 +24,7 @@ def _setup(case, cuda_device, roots=None, hub_threshold=256, chunked=True, chunk
     indptr, adj = can.unique_csr(case.graph)
     assert np.array_equal(hg.indptr, indptr) and np.array_equal(hg.adj, adj)
     dg = G.DeviceGraph(hg, cuda_device)
-    smp = S.WalkSampler(dg, hub_threshold=hub_threshold, chunked=chunked, chunk_walks=chunk_walks)
+    smp = S.WalkSampler(dg, hub_threshold=hub_threshold, algo=algo, chunk_walks=chunk_walks)
     roots = np.arange(case.n, dtype=np.int32) if roots is None else np.asarray(roots, np.int32)
     trees = smp.build_trees(roots)
     emb = S.pad_embedding(case.emb_g, cuda_device)
@@ -95,11 +95,11 @@ def test_stream_replay_matches_reference(name, hub, cuda_device):
         assert got[k] == pf[pp[k]:pp[k + 1]].tolist()
 
 
-def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256, chunked=True, chunk_walks=32):
+def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256, algo="chunk", chunk_walks=32):
     import torch
     from graphgan_b200 import sampler as S
     from oracle import canonical as can
-    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold, chunked, chunk_walks)
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold, algo, chunk_walks)
     par = trees.parent.cpu().numpy()
     E = can.pad_rows(case.emb_g)
     bits = np.zeros(dg.n_bit_words, np.uint32)
@@ -148,12 +148,14 @@ def test_philox_matches_canonical_oracle(name, ratio, hub, cuda_device):
                     hub_threshold=hub)
 
 
+@pytest.mark.parametrize("algo", ["walk", "chunk"])
 @pytest.mark.parametrize("name,hub,ratio", [("rand300", 0, 0.6), ("rand1200", 256, 1.0), ("cagrqc", 8, 1.0)])
-def test_philox_warp_per_walk_kernel(name, hub, ratio, cuda_device):
-    """The un-chunked order-free kernel (one warp per walk) stays available (chunk_ptr = NULL) and agrees too."""
+def test_philox_other_kernels(name, hub, ratio, algo, cuda_device):
+    """Both order-free kernels (one warp per walk -- the default -- and one warp per chunk of walks, here with
+    a ragged chunk size) agree bit for bit."""
     case = loader.load(name)
     _philox_compare(case, cuda_device, None, ratio, seed=4242, n_sample_gen=int(case.n_sample_gen), hub_threshold=hub,
-                    chunked=False)
+                    algo=algo, chunk_walks=5)
 
 
 @pytest.mark.parametrize("hub", [0, 64, 256])
@@ -172,7 +174,7 @@ def test_hub_lists_use_global_scratch(hub, cuda_device):
     rs = np.random.RandomState(0)
     roots = np.sort(rs.choice(np.flatnonzero(hg.degrees() > 0), 400, replace=False))
     cnt, cg = _philox_compare(case, cuda_device, roots, 1.0, seed=99, n_sample_gen=6, hub_threshold=hub,
-                              chunk_walks={0: 32, 64: 8, 256: 5}[hub])
+                              algo={0: "walk", 64: "chunk", 256: "walk"}[hub], chunk_walks=8)
     assert cnt["steps"] > 0
     if hub:   # the reuse must actually remove row gathers
         assert cnt["rows_gathered"] < cnt["raw_sum_l"]
@@ -238,3 +240,43 @@ def test_partition_invariance(cuda_device):
     assert torch.equal(torch.cat([p[1] for p in parts]), fn[:fk])
     assert torch.equal(torch.cat([p[2] for p in parts]), fl[:fk])
     assert torch.equal(dg.d1_bits, bits_full)
+
+
+@pytest.mark.parametrize("d,hub", [(256, 16), (200, 0), (64, 256)])
+def test_wide_and_odd_embeddings(d, hub, cuda_device):
+    """n_emb = 256 (ld 256, 8 float4 chunks per lane), 200 (padded to 224? no: to 256 -> zero columns take part
+    in the canonical dot) and 64, against the canonical oracle."""
+    from graphgan_b200 import graph as G, synth
+    n = 1500
+    edges = synth.power_law(n, 8, seed=12)
+    hg = G.HostGraph(edges, None, n_node=n)
+    case = loader.Case(n=n, dim=d, train_edges=edges, test_edges=np.zeros((0, 2), np.int64),
+                       emb_g=synth.embeddings(n, d, seed=13, sigma=0.25), bias_g=np.random.RandomState(14).normal(0, 0.3, n).astype(np.float32))
+    case["graph"] = [hg.neighbors(i).tolist() for i in range(n)]
+    roots = np.sort(np.random.RandomState(1).choice(np.flatnonzero(hg.degrees() > 0), 300, replace=False))
+    _philox_compare(case, cuda_device, roots, 0.8, seed=321, n_sample_gen=7, hub_threshold=hub, algo="walk")
+
+
+def test_empty_and_degenerate_batches(cuda_device):
+    """Zero roots, roots without walks (isolated nodes, sample_num 0), update_ratio 0: nothing crashes, nothing
+    is accepted, counters stay zero."""
+    import torch
+    from graphgan_b200 import sampler as S
+    case = loader.load("tiny")
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, algo="walk")
+    # (a) no roots at all
+    t0 = S.TreeBatch(trees.roots[:0].contiguous(), trees.parent[:0].contiguous())
+    out = smp.run(emb, bias, t0, dg.raw_deg[:0].contiguous(), True, seed=1)
+    assert out.n_walks == 0 and out.counters_host()["accepted"] == 0
+    c, nb, lb, k = smp.emit_d_rows(out)
+    assert int(k.item()) == 0
+    # (b) only the isolated node 9 and the self-loop-only node 10 (graph_gan.py:252-253)
+    sel = torch.as_tensor([9, 10]).to(cuda_device)
+    t1 = S.TreeBatch(trees.roots[sel].contiguous(), trees.parent[sel].contiguous())
+    out = smp.run(emb, bias, t1, dg.raw_deg[sel].contiguous(), True, seed=1)
+    assert out.root_ok.cpu().tolist()[:2] == [0, 0] and out.counters_host()["accepted"] == 0
+    out = smp.run(emb, bias, t1, 3, False, seed=1, max_path=8)       # G mode: paths_from_i is None
+    assert (out.status.cpu().numpy()[:6] != S.DONE).all()
+    # (c) update_ratio = 0 skips every root
+    out = smp.run(emb, bias, trees, dg.raw_deg, True, seed=1, update_ratio=0.0)
+    assert out.counters_host()["accepted"] == 0 and (out.status.cpu().numpy()[:out.n_walks] == S.SKIPPED).all()
