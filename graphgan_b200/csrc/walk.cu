@@ -65,6 +65,7 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t 
         for (int k = 0; k < UNR; ++k) p[k] = (v[k] >= 0) ? __ldg(par + v[k]) : -2;
 #pragma unroll
         for (int k = 0; k < UNR; ++k) {
+            if (e0 + 32 * k >= a1) break;   // warp-uniform: short adjacency lists use one tile
             const bool isc = p[k] == cur;
             const unsigned mk = __ballot_sync(FULL, isc);
             if (isc) {
@@ -79,7 +80,9 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t 
     const long long t_s = clock64();
     cyc[0] += (unsigned int)(t_s - t_e);
     n_out = n; ids_out = ids; sc_out = sc; m_out = m;
-    if (n == 0) return;
+    // n == 1: softmax = [1.0], cdf = [1.0], and 1.0 > u for every uniform u in [0, 1): the draw is index 0
+    // whatever the score is, so neither the score nor the CDF is computed (leaves of the BFS tree: [father])
+    if (n <= 1) return;
     if (!cached || inc_father) {
         float4 c4[CPL];
         load_row<CPL>(d.emb, d.ld, cur, lane & 7, c4);
@@ -138,9 +141,9 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
 
             // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
             const long long t_c = clock64();
-            const double u = rng.draw((uint32_t)root, k, (uint32_t)step);
+            const double u = rng.draw((uint32_t)root, k, (uint32_t)step);   // the stream mode consumes it regardless
             if (rng.exhausted) { status = GG_NOTRUN; break; }
-            idx = choose_index<false>(sc, n, m, u, lane);
+            idx = (n == 1) ? 0 : choose_index<false>(sc, n, m, u, lane);
             nxt = ids[idx];
             __syncwarp();
             cyc[2] += (unsigned int)(clock64() - t_c);
@@ -320,16 +323,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_chunk_kernel(const
                 if ((grp >> lane) & 1u) status = GG_VOID;
             } else {
                 const long long t_c = clock64();
-                const float S = softmax_exp_sum<false>(sc, n, m, lane);
-                double car[2];
-                const double total = cdf_total<false>(sc, n, S, lane, car);
+                float S = 1.0f;
+                double car[2] = {1.0, 0.0}, total = 1.0;
+                if (n > 1) {
+                    S = softmax_exp_sum<false>(sc, n, m, lane);
+                    total = cdf_total<false>(sc, n, S, lane, car);
+                }
                 const long long a0c = d.indptr[ccur];
                 for (unsigned rest = grp; rest; rest &= rest - 1u) {
                     const int j = __ffs(rest) - 1;
                     const uint32_t kj = __shfl_sync(FULL, k, j);
                     uint32_t a, b;
                     philox4x32_10((uint32_t)root, kj, (uint32_t)cstep, d.pass_tag, k0key, k1key, a, b);
-                    const int idx = cdf_pick<false>(sc, n, S, total, u53(a, b), lane, car);
+                    const int idx = (n == 1) ? 0 : cdf_pick<false>(sc, n, S, total, u53(a, b), lane, car);
                     const int nxt = ids[idx];
                     if (lane == j) {
                         if (cstep == 0) fedge = (int)(a0c + idx);

@@ -114,6 +114,7 @@ __device__ __forceinline__ float softmax_exp_sum(float *sc, int n, float m, int 
         for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; x[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
+            if (t0 + 32 * u >= n) break;            // warp-uniform: no work for the empty tiles of a short list
             const int i = t0 + 32 * u + lane;
             float e = 0.0f;
             if (i < n) { e = exp_c(__fsub_rn(x[u], m)); buf_st<SH>(sc, i, e); }
@@ -136,6 +137,7 @@ __device__ __forceinline__ double cdf_total(const float *sc, int n, float S, int
         for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
+            if (t0 + 32 * u >= n) break;            // warp-uniform
             double x = (double)__fdiv_rn(e[u], S);   // 0 / S == 0 for the padding lanes
             x = warp_scan_ks(x, lane);
             total = __dadd_rn(total, __shfl_sync(FULL, x, 31));
