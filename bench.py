@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--hub-threshold", type=int, default=256, help="degree from which adjacency scores are cached per pass")
     p.add_argument("--algo", default="walk", choices=["chunk", "walk"], help="order-free walk kernel")
     p.add_argument("--chunk-walks", type=int, default=8, help="walks per chunk for --algo chunk")
+    p.add_argument("--depth1", action="store_true", help="enable the per-(root, depth-1 child) CDF reuse (experimental)")
     return p.parse_args()
 
 
@@ -280,7 +281,8 @@ def run_b200(args):
 
     hg, emb_h, roots, d = make_inputs(args, rank)
     dg = G.DeviceGraph(hg, dev)
-    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, algo=args.algo, chunk_walks=args.chunk_walks)
+    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, algo=args.algo, chunk_walks=args.chunk_walks,
+                         depth1=args.depth1)
     emb = S.pad_embedding(emb_h, dev)
     bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
     t0 = time.time()
@@ -397,7 +399,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(roots_pin.numel() * 4),
                     "d2h_bytes_per_step": int(3 * 2 * W * 4 + 8),
                     "call": "WalkSampler.run + finalize + emit_d_rows with pinned host roots in / rows out"},
-            "gpu_launches": (7 if reuse else 5) * args.steps,
+            "gpu_launches": ((9 if smp.depth1 and args.algo == "walk" else 7) if reuse else 5) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "K1 stage: gg::hub_score_kernel + gg::root_cdf_kernel + gg::walk_kernel (ld=%d)" % ld,

@@ -35,6 +35,38 @@ struct Rng {
     }
 };
 
+// children of `cur` among its adjacency entries [a0, a1): U tiles of 32 entries in flight per iteration
+template <int U>
+__device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const int32_t *__restrict__ par, int cur,
+                                                   long long a0, long long a1, bool cached, int *ids, float *sc, int lane,
+                                                   int &n, float &m) {
+    const unsigned lt = (1u << lane) - 1u;
+    for (long long e0 = a0; e0 < a1; e0 += 32 * U) {
+        int v[U], p[U];
+        float cs[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const long long e = e0 + 32 * k + lane;
+            v[k] = (e < a1) ? __ldg(d.adj + e) : -1;
+            cs[k] = (cached && e < a1) ? __ldg(d.edge_score + e) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) p[k] = (v[k] >= 0) ? __ldg(par + v[k]) : -2;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (e0 + 32 * k >= a1) break;   // warp-uniform: short adjacency lists use one tile
+            const bool isc = p[k] == cur;
+            const unsigned mk = __ballot_sync(FULL, isc);
+            if (isc) {
+                const int pos = n + __popc(mk & lt);
+                ids[pos] = v[k];
+                if (cached) { sc[pos] = cs[k]; m = fmaxf(m, cs[k]); }
+            }
+            n += __popc(mk);
+        }
+    }
+}
+
 // Candidate list of `cur` in the tree of the root whose parent array is `par` (graph_gan.py:250-259):
 // [father] + children in adjacency order, with scores all_score[cur, cand] (generator.py:21) -- cached hub
 // scores or the on-demand canonical dot -- and their max.  Warp-cooperative; results are warp-uniform.
@@ -50,32 +82,9 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t 
     int n = 0;
     if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
     float m = -INFINITY;   // running max of the cached scores (lane local)
-    const unsigned lt = (1u << lane) - 1u;
     const long long t_e = clock64();
-    for (long long e0 = a0; e0 < a1; e0 += 32 * UNR) {   // UNR adjacency tiles in flight
-        int v[UNR], p[UNR];
-        float cs[UNR];
-#pragma unroll
-        for (int k = 0; k < UNR; ++k) {
-            const long long e = e0 + 32 * k + lane;
-            v[k] = (e < a1) ? __ldg(d.adj + e) : -1;
-            cs[k] = (cached && e < a1) ? __ldg(d.edge_score + e) : 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < UNR; ++k) p[k] = (v[k] >= 0) ? __ldg(par + v[k]) : -2;
-#pragma unroll
-        for (int k = 0; k < UNR; ++k) {
-            if (e0 + 32 * k >= a1) break;   // warp-uniform: short adjacency lists use one tile
-            const bool isc = p[k] == cur;
-            const unsigned mk = __ballot_sync(FULL, isc);
-            if (isc) {
-                const int pos = n + __popc(mk & lt);
-                ids[pos] = v[k];
-                if (cached) { sc[pos] = cs[k]; m = fmaxf(m, cs[k]); }
-            }
-            n += __popc(mk);
-        }
-    }
+    // (16 tiles in flight for hub adjacency was measured: the extra registers spill and the kernel gets slower)
+    enumerate_children<UNR>(d, par, cur, a0, a1, cached, ids, sc, lane, n, m);
     __syncwarp();
     const long long t_s = clock64();
     cyc[0] += (unsigned int)(t_s - t_e);
@@ -128,8 +137,19 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-253
             const double u = rng.draw((uint32_t)root, k, 0u);
             if (rng.exhausted) { status = GG_NOTRUN; break; }
-            idx = cdf_search(d.root_q + __ldg(d.rq_ptr + slot), n, u);
+            idx = d.first_idx ? __ldg(d.first_idx + w) : cdf_search(d.root_q + __ldg(d.rq_ptr + slot), n, u);
             nxt = __ldg(d.adj + a0 + idx);
+        } else if (step == 1 && d.s1_q) {
+            // ---- depth-1 step from the per-(root, child) CDF (step1_cdf_kernel): walks of a root that picked the
+            // same child share one candidate list; it was built once, each walk only inverts it
+            const long long pos = __ldg(d.rq_ptr + slot) + (fedge - d.indptr[root]);
+            n = __ldg(d.s1_n + pos);
+            if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:255-257
+            inc_father = !d.for_d && !((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u);
+            const double u = rng.draw((uint32_t)root, k, 1u);
+            const long long o = __ldg(d.s1_ptr + pos);
+            idx = (n == 1) ? 0 : cdf_search(d.s1_q + o, n, u);
+            nxt = __ldg(d.s1_ids + o + idx);
         } else {
             // ---- candidate list (graph_gan.py:250-259) + scores
             inc_father = step > 0;
@@ -143,7 +163,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             const long long t_c = clock64();
             const double u = rng.draw((uint32_t)root, k, (uint32_t)step);   // the stream mode consumes it regardless
             if (rng.exhausted) { status = GG_NOTRUN; break; }
-            idx = (n == 1) ? 0 : choose_index<false>(sc, n, m, u, lane);
+            idx = (n == 1) ? 0 : choose_index<false>(sc, n, m, u, lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
             nxt = ids[idx];
             __syncwarp();
             cyc[2] += (unsigned int)(clock64() - t_c);
@@ -168,6 +188,65 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
     }
     if (status == GG_DONE && d.max_path > 0 && plen > d.max_path) overflow += 1;
     return status;
+}
+
+// ---------------------------------------------------------------- depth-1 reuse (Philox mode)
+// root_step_kernel: the root step of every walk (one thread per walk inverts the root's CDF) and a count of
+// the walks per (root, depth-1 child).  step1_cdf_kernel: for every pair that was picked at least once, the
+// child's candidate list / softmax / normalised CDF, built ONCE (walk_kernel then inverts it per walk).
+__global__ void root_step_kernel(const __grid_constant__ gg_walk_desc d) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= d.n_walks) return;
+    const int slot = __ldg(d.walk_slot + w);
+    const int root = d.roots[slot];
+    const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
+    const uint32_t k0 = (uint32_t)d.seed, k1 = (uint32_t)(d.seed >> 32);
+    uint32_t a, b;
+    if (d.update_ratio < 1.0) {
+        philox4x32_10((uint32_t)root, 0xffffffffu, 0u, d.pass_tag, k0, k1, a, b);
+        if (!(u53(a, b) < d.update_ratio)) { d.first_idx[w] = -2; return; }
+    }
+    const long long a0 = d.indptr[root];
+    const int n = (int)(d.indptr[root + 1] - a0);
+    if (n == 0) { d.first_idx[w] = -1; return; }
+    philox4x32_10((uint32_t)root, k, 0u, d.pass_tag, k0, k1, a, b);
+    const long long o = __ldg(d.rq_ptr + slot);
+    const int idx = cdf_search(d.root_q + o, n, u53(a, b));
+    d.first_idx[w] = idx;
+    atomicAdd(d.s1_cnt + o + idx, 1);
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) step1_cdf_kernel(const __grid_constant__ gg_walk_desc d) {
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
+    int *s_ids = reinterpret_cast<int *>(s_sc + SC_CAP);
+    const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
+    const long long nwarps = (long long)gridDim.x * WARPS_PER_CTA;
+    int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
+    float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
+    unsigned long long rows_gathered = 0;
+    unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (long long pos = gw; pos < d.s1_nq; pos += nwarps) {
+        if (__ldg(d.s1_cnt + pos) == 0) continue;
+        const int slot = __ldg(d.s1_slot + pos);
+        const int root = d.roots[slot];
+        const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
+        const long long e = d.indptr[root] + (pos - __ldg(d.rq_ptr + slot));
+        const int c = __ldg(d.adj + e);
+        const bool inc_father = !d.for_d && !((d.d1_bits[e >> 5] >> (e & 31)) & 1u);   // graph_gan.py:258-259
+        int n; float m; int *ids; float *sc;
+        build_list<CPL>(d, par, c, root, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
+        if (lane == 0) d.s1_n[pos] = n;
+        if (n == 0) continue;
+        const long long o = __ldg(d.s1_ptr + pos);
+        for (int i = lane; i < n; i += 32) d.s1_ids[o + i] = ids[i];
+        if (n == 1) { if (lane == 0) d.s1_q[o] = 1.0; }
+        else cdf_store_m(sc, n, m, d.s1_q + o, lane);
+        __syncwarp();
+    }
+    if (lane == 0 && rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
 }
 
 // ---------------------------------------------------------------- order-free (Philox) kernel
@@ -534,6 +613,26 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
     } else {
         const int ctas = gg::grid_ctas();
         GG_REQUIRE(d.scratch_bytes >= (int64_t)ctas * gg::WARPS_PER_CTA * 2 * d.max_cand * 4, "scratch too small");
+        if (d.s1_q) {   // depth-1 reuse: root steps + one CDF per (root, child) pair that occurs
+            GG_REQUIRE(d.root_q && d.walk_slot && d.first_idx && d.s1_cnt && d.s1_n && d.s1_ptr && d.s1_ids && d.s1_slot,
+                       "depth-1 reuse needs root_q, walk_slot and the s1_* buffers");
+            GG_CHECK(cudaMemsetAsync(d.s1_cnt, 0, sizeof(int32_t) * (size_t)d.s1_nq, st));
+            gg::root_step_kernel<<<(unsigned)((d.n_walks + 255) / 256), 256, 0, st>>>(d);
+            GG_CHECK(cudaGetLastError());
+#define GG_S1(C)                                                                                                      \
+    GG_CHECK(cudaFuncSetAttribute(gg::step1_cdf_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                  gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                      \
+    gg::step1_cdf_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d)
+            switch (cpl) {
+                case 1: GG_S1(1); break;
+                case 2: GG_S1(2); break;
+                case 4: GG_S1(4); break;
+                case 8: GG_S1(8); break;
+                default: gg::set_error("gg_walk_sample: unsupported ld %d (supported: 32, 64, 128, 256)", d.ld); return 2;
+            }
+#undef GG_S1
+            GG_CHECK(cudaGetLastError());
+        }
         if (d.chunk_ptr) {
             GG_REQUIRE(d.n_chunks >= 0 && d.n_chunks < (1ll << 32), "bad chunk count");
             GG_REQUIRE(d.chunk_walks >= 1 && d.chunk_walks <= 32, "chunk_walks must be in [1, 32]");

@@ -105,15 +105,15 @@ __device__ __forceinline__ float list_max(const float *sc, int n, int lane) {
 // softmax numerators in place (sc[i] <- e_i = exp_c(s_i - m)) and their canonical sum
 // S = T_0 + T_1 + ... (tile sums by butterfly; 0 + T_0 == T_0 and S + 0 == S exactly, so empty
 // tiles of the unrolled tail are harmless).  UNR tiles are in flight per iteration.
-template <bool SH>
+template <bool SH, int U = UNR>
 __device__ __forceinline__ float softmax_exp_sum(float *sc, int n, float m, int lane) {
     float S = 0.0f;
-    for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
-        float x[UNR];
+    for (int t0 = 0; t0 < n; t0 += 32 * U) {
+        float x[U];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; x[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
+        for (int u = 0; u < U; ++u) { const int i = t0 + 32 * u + lane; x[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (t0 + 32 * u >= n) break;            // warp-uniform: no work for the empty tiles of a short list
             const int i = t0 + 32 * u + lane;
             float e = 0.0f;
@@ -127,16 +127,16 @@ __device__ __forceinline__ float softmax_exp_sum(float *sc, int n, float m, int 
 
 // total of the float64 CDF over p_i = e_i / S.  Lane (t & 31) also keeps the running total after tile t
 // in car[t >> 5] (tiles 0..63), so that the draw can jump straight to the tile that contains it.
-template <bool SH>
+template <bool SH, int U = UNR>
 __device__ __forceinline__ double cdf_total(const float *sc, int n, float S, int lane, double (&car)[2]) {
     double total = 0.0;
     car[0] = car[1] = 0.0;
-    for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
-        float e[UNR];
+    for (int t0 = 0; t0 < n; t0 += 32 * U) {
+        float e[U];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
+        for (int u = 0; u < U; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (t0 + 32 * u >= n) break;            // warp-uniform
             double x = (double)__fdiv_rn(e[u], S);   // 0 / S == 0 for the padding lanes
             x = warp_scan_ks(x, lane);
@@ -193,15 +193,76 @@ __device__ __forceinline__ int cdf_pick(const float *sc, int n, float S, double 
 }
 
 // softmax + CDF + draw over sc[0..n) given its max m (== ggo_choose).  All lanes return the index.
+// Long lists (global scratch): running total after EVERY tile goes to `tiles` (the warp's idle shared score buffer
+// viewed as doubles), so the draw can locate its tile among hundreds without a linear scan.
+__device__ __forceinline__ double cdf_total_tiles(const float *sc, int n, float S, int lane, double *tiles) {
+    constexpr int U = 16;
+    double total = 0.0;
+    for (int t0 = 0; t0 < n; t0 += 32 * U) {
+        float e[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? sc[i] : 0.0f; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (t0 + 32 * u >= n) break;
+            double x = (double)__fdiv_rn(e[u], S);
+            x = warp_scan_ks(x, lane);
+            total = __dadd_rn(total, __shfl_sync(FULL, x, 31));
+            if (lane == 0) tiles[(t0 >> 5) + u] = total;
+        }
+    }
+    __syncwarp();
+    return total;
+}
+__device__ __forceinline__ int cdf_pick_tiles(const float *sc, int n, float S, double total, double u, int lane,
+                                              const double *tiles) {
+    const int ntiles = (n + 31) >> 5;
+    for (int tb = 0; tb < ntiles; tb += 32) {
+        const int t = tb + lane;
+        const bool p = (t < ntiles) && (__ddiv_rn(tiles[t], total) > u);
+        const unsigned mk = __ballot_sync(FULL, p);
+        if (mk) {
+            const int t_hit = tb + __ffs(mk) - 1;
+            return cdf_pick_from<false>(sc, n, S, total, u, lane, t_hit, t_hit > 0 ? tiles[t_hit - 1] : 0.0);
+        }
+    }
+    return n - 1;
+}
+
 template <bool SH>
-__device__ __forceinline__ int choose_index(float *sc, int n, float m, double u, int lane) {
-    const float S = softmax_exp_sum<SH>(sc, n, m, lane);
-    double car[2];
-    const double total = cdf_total<SH>(sc, n, S, lane, car);
+__device__ __forceinline__ int choose_index(float *sc, int n, float m, double u, int lane, double *tiles = nullptr) {
+    float S;
+    double car[2], total;
+    if (n > SC_CAP && tiles && ((n + 31) >> 5) <= SC_CAP / 2) {
+        // the list lives in global scratch: 16 tiles in flight per pass, per-tile totals in shared memory
+        S = softmax_exp_sum<SH, 16>(sc, n, m, lane);
+        total = cdf_total_tiles(sc, n, S, lane, tiles);
+        return cdf_pick_tiles(sc, n, S, total, u, lane, tiles);
+    }
+    if (n > SC_CAP) {
+        S = softmax_exp_sum<SH, 16>(sc, n, m, lane);
+        total = cdf_total<SH, 16>(sc, n, S, lane, car);
+    } else {
+        S = softmax_exp_sum<SH>(sc, n, m, lane);
+        total = cdf_total<SH>(sc, n, S, lane, car);
+    }
     return cdf_pick<SH>(sc, n, S, total, u, lane, car);
 }
 
 // normalised CDF q_i = cdf_i / total written out (the array numpy's choice would searchsorted)
+__device__ __forceinline__ void cdf_store_m(float *sc, int n, float m, double *q_out, int lane) {
+    const float S = softmax_exp_sum<false>(sc, n, m, lane);
+    double car[2];
+    const double total = cdf_total<false>(sc, n, S, lane, car);
+    double carry = 0.0;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int i = t0 + lane;
+        double x = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;
+        x = warp_scan_ks(x, lane);
+        if (i < n) q_out[i] = __ddiv_rn(__dadd_rn(carry, x), total);
+        carry = __dadd_rn(carry, __shfl_sync(FULL, x, 31));
+    }
+}
 __device__ __forceinline__ void cdf_store(float *sc, int n, double *q_out, int lane) {
     const float m = list_max<false>(sc, n, lane);
     const float S = softmax_exp_sum<false>(sc, n, m, lane);

@@ -83,9 +83,11 @@ class WalkPlan:
         r = trees.roots.long()
         self.rq_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
         self.rq_ptr[1:] = torch.cumsum(g.indptr[r + 1] - g.indptr[r], 0)       # prefix of the roots' walk degrees
-        nq = max(int(self.rq_ptr[-1].item()), 1)
+        self.nq = int(self.rq_ptr[-1].item())
+        nq = max(self.nq, 1)
         self.root_q = torch.empty(nq, dtype=torch.float64, device=dev)
         self.root_sc = torch.empty(nq, dtype=torch.float32, device=dev)
+        self._s1 = None
         W = max(self.n_walks, 1)
         i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
         self.samples, self.status, self.first_edge, self.wsteps, self.wsuml = i32(W), i32(W), i32(W), i32(W), i32(W)
@@ -98,8 +100,27 @@ class WalkPlan:
         self.rows = [i32(max(2 * self.n_walks, 1)) for _ in range(3)] if for_d else None
 
 
+    def depth1_buffers(self, sampler):
+        """Static layout of the depth-1 CDF cache (csrc/walk.cu: step1_cdf_kernel): one slice of degree(child) + 1
+        entries per (root, neighbour) pair.  Built on first use (plumbing: gathers + one cumsum)."""
+        if self._s1 is None:
+            torch, g, dev = sampler.torch, sampler.g, sampler.device
+            deg_r = self.rq_ptr[1:] - self.rq_ptr[:-1]
+            slot = torch.repeat_interleave(torch.arange(self.n_roots, dtype=torch.int32, device=dev), deg_r, output_size=self.nq)
+            r = self.trees.roots.long()[slot.long()]
+            ent = g.indptr[r] + (torch.arange(self.nq, dtype=torch.int64, device=dev) - self.rq_ptr[slot.long()])
+            c = g.adj[ent].long()
+            ptr_ = torch.zeros(self.nq + 1, dtype=torch.int64, device=dev)
+            ptr_[1:] = torch.cumsum(g.indptr[c + 1] - g.indptr[c] + 1, 0)
+            total = max(int(ptr_[-1].item()), 1)
+            i32 = lambda k: torch.empty(max(k, 1), dtype=torch.int32, device=dev)
+            self._s1 = dict(slot=slot, ptr=ptr_, cnt=i32(self.nq), n=i32(self.nq), ids=i32(total),
+                            q=torch.empty(total, dtype=torch.float64, device=dev), first=i32(self.n_walks))
+        return self._s1
+
+
 class WalkSampler:
-    def __init__(self, graph, hub_threshold=256, algo="walk", chunk_walks=8):
+    def __init__(self, graph, hub_threshold=256, algo="walk", chunk_walks=8, depth1=False):
         import torch
         self.torch = torch
         self.g = graph
@@ -112,6 +133,10 @@ class WalkSampler:
         assert algo in ("chunk", "walk")
         self.algo = algo
         self.chunk_walks = int(chunk_walks)
+        # one CDF per (root, depth-1 child) pair that occurs (needs reuse).  Off by default: on C3 it halves the walk
+        # kernel (1.79 -> 1.08 ms) but the kernel that builds the CDFs takes 1.39 ms, because a 13.8k-entry hub list
+        # is built by a single warp (~1 ms) -- it needs a CTA-cooperative path for giant lists first
+        self.depth1 = bool(depth1)
         nbytes = C.c_int64(0)
         _cabi.check(self.lib.gg_walk_scratch_bytes(self.max_cand, C.byref(nbytes)), "gg_walk_scratch_bytes")
         self.scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
@@ -161,6 +186,10 @@ class WalkSampler:
         if reuse:
             self.g.hub_tiles(self.hub_threshold)
             d.edge_score, d.hub_threshold, d.root_q = ptr(self.g.edge_score), self.hub_threshold, ptr(plan.root_q)
+            if self.depth1 and rng_mode == RNG_PHILOX and plan.nq > 0 and plan.n_walks > 0 and self.algo == "walk":
+                b = plan.depth1_buffers(self)
+                d.s1_nq, d.s1_slot, d.s1_ptr, d.s1_cnt, d.s1_n = plan.nq, ptr(b["slot"]), ptr(b["ptr"]), ptr(b["cnt"]), ptr(b["n"])
+                d.s1_q, d.s1_ids, d.first_idx = ptr(b["q"]), ptr(b["ids"]), ptr(b["first"])
         return d
 
     def precompute(self, emb, bias, plan, desc=None):

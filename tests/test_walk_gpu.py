@@ -11,7 +11,7 @@ from tests.golden import loader
 pytestmark = pytest.mark.gpu
 
 
-def _setup(case, cuda_device, roots=None, hub_threshold=256, algo="chunk", chunk_walks=32):
+def _setup(case, cuda_device, roots=None, hub_threshold=256, algo="chunk", chunk_walks=32, depth1=True):
     import torch
     from graphgan_b200 import graph as G, sampler as S
     from oracle import canonical as can
@@ -24,7 +24,7 @@ def _setup(case, cuda_device, roots=None, hub_threshold=256, algo="chunk", chunk
     indptr, adj = can.unique_csr(case.graph)
     assert np.array_equal(hg.indptr, indptr) and np.array_equal(hg.adj, adj)
     dg = G.DeviceGraph(hg, cuda_device)
-    smp = S.WalkSampler(dg, hub_threshold=hub_threshold, algo=algo, chunk_walks=chunk_walks)
+    smp = S.WalkSampler(dg, hub_threshold=hub_threshold, algo=algo, chunk_walks=chunk_walks, depth1=depth1)
     roots = np.arange(case.n, dtype=np.int32) if roots is None else np.asarray(roots, np.int32)
     trees = smp.build_trees(roots)
     emb = S.pad_embedding(case.emb_g, cuda_device)
@@ -196,7 +196,7 @@ def test_giant_hub_lists_beyond_the_smem_score_buffer(hub, cuda_device):
     assert hg.max_deg >= n - 1
     emb_h = synth.embeddings(n, d, seed=10, sigma=0.4)
     dg = G.DeviceGraph(hg, cuda_device)
-    smp = S.WalkSampler(dg, hub_threshold=hub)
+    smp = S.WalkSampler(dg, hub_threshold=hub, depth1=True)
     roots = np.asarray([0, 3, 11, 200, 1999, 3599], np.int32)
     trees = smp.build_trees(roots)
     par = trees.parent.cpu().numpy()
