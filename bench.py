@@ -187,7 +187,8 @@ class CpuReference:
         e, st, sl, dt = _sample_chunk((0, 2, 12345))
         per_root = max(dt / 2, 1e-4)
         n = int(min(len(roots), max(2 * workers, workers * seconds / per_root)))
-        n = min(n, 96 * workers)                      # bound the tree memory / BFS time of the sample
+        # bound the tree memory (4*N bytes per root) and, when the trees are built here, the BFS time of the sample
+        n = min(n, 1024 if parent_rows is not None else 96 * workers)
         self.sample = roots[np.unique(np.linspace(0, len(roots) - 1, n).astype(np.int64))]
         n = len(self.sample)
         _SH["sample"] = self.sample
