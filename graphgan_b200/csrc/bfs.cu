@@ -36,38 +36,44 @@ __host__ __device__ inline long long bfs_words_per_cta(long long n, long long nn
 }
 
 // exclusive scan of f(i), i in [0,n), into out[0..n]; returns total (block-wide, all threads).
+// Every warp scans one contiguous chunk with a running carry (coalesced, no block barrier inside the loop);
+// the 32 chunk totals are scanned once; a second sweep adds the chunk offsets.  Three barriers in total --
+// the frontier of a level can have ~N entries, and a barrier per 1024 elements used to dominate the build.
 template <typename F>
 __device__ unsigned block_exclusive_scan(F f, unsigned *out, unsigned n, unsigned *s_warp, unsigned *s_carry) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) *s_carry = 0;
-    __syncthreads();
-    for (unsigned base = 0; base < n; base += BFS_THREADS) {
-        const unsigned i = base + threadIdx.x;
-        const unsigned v = (i < n) ? f(i) : 0u;
+    const unsigned chunk = ((n + BFS_WARPS - 1) / BFS_WARPS + 31u) & ~31u;
+    const unsigned lo = wid * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+    unsigned carry = 0;
+    for (unsigned base = lo; base < hi; base += 32) {
+        const unsigned i = base + lane;
+        const unsigned v = (i < hi) ? f(i) : 0u;
         unsigned x = v;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const unsigned y = __shfl_up_sync(FULL, x, off);
             if (lane >= off) x += y;
         }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned t = s_warp[lane];
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned y = __shfl_up_sync(FULL, t, off);
-                if (lane >= off) t += y;
-            }
-            s_warp[lane] = t;
-        }
-        __syncthreads();
-        const unsigned before = *s_carry + (wid ? s_warp[wid - 1] : 0u) + (x - v);
-        if (i < n) out[i] = before;
-        __syncthreads();
-        if (threadIdx.x == BFS_THREADS - 1) *s_carry = before + v;
-        __syncthreads();
+        if (i < hi) out[i] = carry + x - v;
+        carry += __shfl_sync(FULL, x, 31);
     }
+    if (lane == 0) s_warp[wid] = carry;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned v = s_warp[lane];
+        unsigned t = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned y = __shfl_up_sync(FULL, t, off);
+            if (lane >= off) t += y;
+        }
+        s_warp[lane] = t - v;                 // exclusive offset of every chunk
+        if (lane == 31) *s_carry = t;         // grand total
+    }
+    __syncthreads();
+    const unsigned add = s_warp[wid];
+    if (add)
+        for (unsigned i = lo + lane; i < hi; i += 32) out[i] += add;
     const unsigned total = *s_carry;
     if (threadIdx.x == 0) out[n] = total;
     __syncthreads();
@@ -124,9 +130,13 @@ bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr
                 const long long a0 = indptr[u];
                 const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
                 if (dg > 32) { big[atomicAdd(&s_nbig, 1u)] = i; continue; }
-                for (unsigned j = 0; j < dg; ++j) {
-                    const int v = __ldg(adj + a0 + j);
-                    if (!((bm[v >> 5] >> (v & 31)) & 1u)) atomicMin(claim + v, q0 + j);
+                for (unsigned j0 = 0; j0 < dg; j0 += 8) {   // 8 independent adjacency loads in flight per thread
+                    int v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = (j0 + k < dg) ? __ldg(adj + a0 + j0 + k) : -1;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (v[k] >= 0 && !((bm[v[k] >> 5] >> (v[k] & 31)) & 1u)) atomicMin(claim + v[k], q0 + j0 + k);
                 }
             }
             __syncthreads();
@@ -153,9 +163,17 @@ bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr
                 const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
                 if (dg > 32) continue;
                 unsigned mk = 0;
-                for (unsigned j = 0; j < dg; ++j) {
-                    const int v = __ldg(adj + a0 + j);
-                    if (!((bm[v >> 5] >> (v & 31)) & 1u) && __ldcg(claim + v) == q0 + j) mk |= 1u << j;
+                for (unsigned j0 = 0; j0 < dg; j0 += 8) {
+                    int v[8];
+                    unsigned cl[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = (j0 + k < dg) ? __ldg(adj + a0 + j0 + k) : -1;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        cl[k] = (v[k] >= 0 && !((bm[v[k] >> 5] >> (v[k] & 31)) & 1u)) ? __ldcg(claim + v[k]) : 0u;   // q >= 1
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (cl[k] == q0 + j0 + k) mk |= 1u << (j0 + k);
                 }
                 if (dg) wmask[woff[i]] = mk;
                 base[i] = __popc(mk);
