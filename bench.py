@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--hub-threshold", type=int, default=256, help="degree from which adjacency scores are cached per pass")
     p.add_argument("--algo", default="walk", choices=["chunk", "walk"], help="order-free walk kernel")
     p.add_argument("--chunk-walks", type=int, default=8, help="walks per chunk for --algo chunk")
+    p.add_argument("--file-order", action="store_true", help="start the walks in root order instead of hub-neighbourhoods first")
     p.add_argument("--depth1", action="store_true", help="enable the per-(root, depth-1 child) CDF reuse (experimental)")
     return p.parse_args()
 
@@ -283,7 +284,7 @@ def run_b200(args):
     hg, emb_h, roots, d = make_inputs(args, rank)
     dg = G.DeviceGraph(hg, dev)
     smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, algo=args.algo, chunk_walks=args.chunk_walks,
-                         depth1=args.depth1)
+                         depth1=args.depth1, hub_first=not args.file_order)
     emb = S.pad_embedding(emb_h, dev)
     bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
     t0 = time.time()

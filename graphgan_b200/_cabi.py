@@ -32,7 +32,7 @@ class WalkDesc(C.Structure):
         ("hub_threshold", C.c_int32), ("chunk_walks", C.c_int32),
         ("chunk_ptr", C.c_void_p), ("n_chunks", C.c_int64), ("walk_slot", C.c_void_p),
         ("s1_nq", C.c_int64), ("s1_slot", C.c_void_p), ("s1_ptr", C.c_void_p), ("s1_cnt", C.c_void_p), ("s1_n", C.c_void_p),
-        ("s1_q", C.c_void_p), ("s1_ids", C.c_void_p), ("first_idx", C.c_void_p),
+        ("s1_q", C.c_void_p), ("s1_ids", C.c_void_p), ("first_idx", C.c_void_p), ("walk_order", C.c_void_p),
     ]
 
 
@@ -57,6 +57,8 @@ SIGNATURES = {
     "gg_adam_apply": (C.c_int, [_I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),
     "gg_train_steps": (C.c_int, [_I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P,
                                 _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
+    "gg_train_loop": (C.c_int, [_I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P,
+                               _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
     "gg_window_pairs": (C.c_int, [_I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _P]),
 }
 

@@ -9,7 +9,7 @@
 // 64-pair step streams all of E, m, v: 24 * N * ld bytes -- a pure HBM-bandwidth kernel.
 // One warp per row (float4 per lane at ld = 128); the row -> gradient-slot map written by
 // gg_pair_grad tells whether the row has a gradient, and is reset here.
-#include "gg_common.cuh"
+#include "update_dev.cuh"
 
 namespace gg {
 namespace {
@@ -20,41 +20,7 @@ __global__ void __launch_bounds__(256) adam_kernel(long long n_node, int ld, flo
                                                    float *__restrict__ v_bias, const float *__restrict__ grad_rows,
                                                    const float *__restrict__ grad_bias, int *__restrict__ row_slot,
                                                    float lr_t, float b1, float b2, float eps) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
-    for (long long row = warp; row < n_node; row += nwarps) {
-        int slot = -1;
-        if (lane == 0) slot = row_slot[row];
-        slot = __shfl_sync(FULL, slot, 0);
-        const size_t ro = (size_t)row * ld;
-        for (int c = 4 * lane; c < ld; c += 128) {
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (slot >= 0) g = *reinterpret_cast<const float4 *>(grad_rows + (size_t)slot * ld + c);
-            float4 m = *reinterpret_cast<float4 *>(m_emb + ro + c);
-            float4 v = *reinterpret_cast<float4 *>(v_emb + ro + c);
-            float4 x = *reinterpret_cast<float4 *>(emb + ro + c);
-// TF1.8 op order (assign m*b1; scatter_add (1-b1)*g; ... var -= lr*m/(sqrt(v)+eps)), no contraction
-#define GG_ADAM1(f)                                                                                   \
-    m.f = __fadd_rn(__fmul_rn(m.f, b1), __fmul_rn(omb1, g.f));                                        \
-    v.f = __fadd_rn(__fmul_rn(v.f, b2), __fmul_rn(__fmul_rn(omb2, g.f), g.f));                        \
-    x.f = __fsub_rn(x.f, __fdiv_rn(__fmul_rn(lr_t, m.f), __fadd_rn(__fsqrt_rn(v.f), eps)));
-            GG_ADAM1(x) GG_ADAM1(y) GG_ADAM1(z) GG_ADAM1(w)
-#undef GG_ADAM1
-            *reinterpret_cast<float4 *>(m_emb + ro + c) = m;
-            *reinterpret_cast<float4 *>(v_emb + ro + c) = v;
-            *reinterpret_cast<float4 *>(emb + ro + c) = x;
-        }
-        if (lane == 0) {
-            const float g = slot >= 0 ? grad_bias[slot] : 0.0f;
-            const float m = __fadd_rn(__fmul_rn(m_bias[row], b1), __fmul_rn(omb1, g));
-            const float v = __fadd_rn(__fmul_rn(v_bias[row], b2), __fmul_rn(__fmul_rn(omb2, g), g));
-            m_bias[row] = m; v_bias[row] = v;
-            bias[row] = __fsub_rn(bias[row], __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(__fsqrt_rn(v), eps)));
-            if (slot >= 0) row_slot[row] = -1;
-        }
-    }
+    adam_rows<false>(n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, grad_rows, grad_bias, row_slot, lr_t, b1, b2, eps);
 }
 
 }  // namespace

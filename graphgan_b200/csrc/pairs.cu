@@ -9,7 +9,7 @@
 // unique row ids + per-row sums (entries accumulated in (i-side 0..B-1, j-side 0..B-1) order,
 // deterministic).  A mini-batch is tiny (config.batch_size_* = 64), so one CTA does it; the
 // expensive part of a step is K3's dense sweep (adam.cu).  Gather-bound, fp32, no tensor cores.
-#include "gg_common.cuh"
+#include "update_dev.cuh"
 
 namespace gg {
 namespace {
@@ -56,116 +56,14 @@ __global__ void __launch_bounds__(256) all_score_kernel(long long n, const float
 }
 
 // ---------------------------------------------------------------- mini-batch gradient (1 CTA)
-constexpr int GRAD_THREADS = 1024;
-
 __global__ void __launch_bounds__(GRAD_THREADS, 1)
 pair_grad_kernel(int mode, int B, int batch_total, const int *__restrict__ ni, const int *__restrict__ nj, const float *__restrict__ aux,
                  const float *__restrict__ emb, const float *__restrict__ bias, int ld, float lambda,
                  int *__restrict__ n_unique, int *__restrict__ uniq_ids, float *__restrict__ grad_rows,
                  float *__restrict__ grad_bias, int *__restrict__ row_slot) {
     extern __shared__ int smem[];
-    int *ids = smem;              // [2B]  entry -> row id (i-side entries first, then j-side)
-    int *slot = ids + 2 * B;      // [2B]  entry -> unique slot
-    float *delta = reinterpret_cast<float *>(slot + 2 * B);  // [B] dL/dscore_k
-    __shared__ int s_warp[32];
-    __shared__ int s_total;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, grp = lane >> 3, g = lane & 7;
-    const int E = 2 * B;
-    for (int t = tid; t < E; t += GRAD_THREADS) ids[t] = (t < B) ? ni[t] : nj[t - B];
-    // ---- forward: score and dL/dscore
-    for (int k0 = wid * 4; k0 < B; k0 += (GRAD_THREADS / 32) * 4) {
-        const int k = k0 + grp;
-        const bool valid = k < B;
-        const int i = valid ? ni[k] : 0, j = valid ? nj[k] : 0;
-        float s = group_dot(emb + (size_t)i * ld, emb + (size_t)j * ld, ld, g);
-        if (valid && g == 0) {
-            s = __fadd_rn(s, bias[j]);
-            const float p = (float)(1.0 / (1.0 + exp(-(double)s)));   // sigmoid (B values: fp64 costs nothing)
-            float d;
-            if (mode == 0) {
-                d = p - aux[k];                          // d/ds sigmoid_xent(label, s) = sigmoid(s) - label
-            } else {
-                // d/ds [-(1/B) r log(clip(p,1e-5,1))] = -(r/B)(1-p) where the clip passes (p >= 1e-5)
-                d = (p >= 1e-5f) ? -(aux[k] / (float)batch_total) * (1.0f - p) : 0.0f;
-            }
-            delta[k] = d;
-        }
-    }
-    __syncthreads();
-    // ---- unique: first occurrence of every row id gets a slot, in entry order
-    int is_first = 0, first_t = 0;
-    // (one entry per thread per round; E <= 2*GG_MAX_BATCH = 2*GRAD_THREADS)
-    int base_total = 0;
-    for (int t0 = 0; t0 < E; t0 += GRAD_THREADS) {
-        const int t = t0 + tid;
-        is_first = 0; first_t = t;
-        if (t < E) {
-            const int id = ids[t];
-            int f = t;
-            for (int q = 0; q < t; ++q) if (ids[q] == id) { f = q; break; }
-            first_t = f; is_first = (f == t);
-        }
-        int x = is_first;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int y = __shfl_up_sync(FULL, x, off);
-            if (lane >= off) x += y;
-        }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            int v = s_warp[lane];
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int y = __shfl_up_sync(FULL, v, off);
-                if (lane >= off) v += y;
-            }
-            s_warp[lane] = v;
-        }
-        __syncthreads();
-        const int excl = base_total + (wid ? s_warp[wid - 1] : 0) + x - is_first;
-        if (t < E) slot[t] = is_first ? excl : -1 - first_t;  // non-first: remember where the first is
-        if (t < E && is_first) { uniq_ids[excl] = ids[t]; row_slot[ids[t]] = excl; }
-        base_total += s_warp[31];
-        __syncthreads();
-    }
-    if (tid == 0) { s_total = base_total; *n_unique = base_total; }
-    __syncthreads();
-    for (int t = tid; t < E; t += GRAD_THREADS) if (slot[t] < 0) { const int f = -1 - slot[t]; slot[t] = slot[f] < 0 ? -1 : slot[f]; }
-    __syncthreads();
-    const int U = s_total;
-    // ---- segment sums: slot u accumulates its entries in entry order
-    for (int u = wid; u < U; u += GRAD_THREADS / 32) {
-        const int row = uniq_ids[u];
-        const float *erow = emb + (size_t)row * ld;
-        for (int c = 4 * lane; c < ld; c += 128) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 self = ldg4(erow + c);
-            for (int t = 0; t < E; ++t) {
-                if (slot[t] != u) continue;
-                const int k = (t < B) ? t : t - B;
-                const int other = (t < B) ? nj[k] : ni[k];
-                const float4 o = ldg4(emb + (size_t)other * ld + c);
-                const float d = delta[k];
-                // d(score)/d(this row) = other row;  l2 term: lambda * this row, once per occurrence.
-                // Explicit mul/mul/add/add (no fma contraction): the same op sequence as the IndexedSlices
-                // sum of the numpy oracle, so cancellation noise in near-zero coordinates stays comparable.
-#define GG_ACC(f) acc.f = __fadd_rn(acc.f, __fadd_rn(__fmul_rn(d, o.f), __fmul_rn(lambda, self.f)))
-                GG_ACC(x); GG_ACC(y); GG_ACC(z); GG_ACC(w);
-#undef GG_ACC
-            }
-            *reinterpret_cast<float4 *>(grad_rows + (size_t)u * ld + c) = acc;
-        }
-        if (lane == 0) {
-            float gb = 0.0f;
-            const float bself = bias[row];
-            for (int t = B; t < E; ++t) {
-                if (slot[t] != u) continue;
-                gb = __fadd_rn(gb, mode == 0 ? __fadd_rn(delta[t - B], __fmul_rn(lambda, bself)) : delta[t - B]);  // generator.py:28-29: no bias l2
-            }
-            grad_bias[u] = gb;
-        }
-    }
+    pair_grad_body<false>(smem, mode, B, batch_total, ni, nj, aux, emb, bias, ld, lambda, n_unique, uniq_ids, grad_rows, grad_bias,
+                          row_slot);
 }
 
 // ---------------------------------------------------------------- data-parallel merge (1 CTA)

@@ -5,7 +5,7 @@
 // walks the caller's shuffled start list and enqueues every step on the stream; nothing synchronises.
 #include <math.h>
 
-#include "gg_common.cuh"
+#include "update_dev.cuh"
 
 extern "C" int gg_train_steps(int32_t mode, int64_t n_rows, const int64_t *start_list, int64_t n_starts, int32_t batch_size,
                               const int32_t *node_id, const int32_t *node_neighbor_id, const float *aux, int64_t n_node,
@@ -31,6 +31,120 @@ extern "C" int gg_train_steps(int32_t mode, int64_t n_rows, const int64_t *start
         rc = gg_adam_apply(n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, n_unique, uniq_ids, grad_rows, grad_bias,
                            row_slot, lr_t, beta1, beta2, eps, stream);
         if (rc) return rc;
+        volatile float p1 = *beta1_power * beta1, p2 = *beta2_power * beta2;
+        *beta1_power = p1;
+        *beta2_power = p2;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- persistent step loop (f3)
+// The same steps as above in ONE cooperative launch (co-residency is what the cooperative launch buys; the
+// barriers are hand-rolled because the dependence is one-to-all then all-to-one, not all-to-all):
+//   CTA 0 computes the mini-batch gradient (K2 body) and publishes `ready = s+1` (release store);
+//   every CTA waits for that flag (acquire load), runs its share of the dense Adam sweep (K3 body) and
+//   adds 1 to `done` (release add);  CTA 0 alone waits for done == gridDim.x*(s+1) before the next gradient.
+// Parameters written in one step are read in the next by another SM, so cross-SM reads go through L2 (the
+// COH = true bodies); a row of m/v/emb is always swept by the same warp.  Bit-identical to gg_train_steps.
+namespace gg {
+namespace {
+
+struct LoopArgs {
+    int mode, batch_size, ld;
+    long long n_rows, n_starts, n_node;
+    const long long *starts;
+    const int *node_id, *node_neighbor_id;
+    const float *aux;
+    float *emb, *m_emb, *v_emb, *bias, *m_bias, *v_bias;
+    float lambda;
+    int *n_unique, *uniq_ids;
+    float *grad_rows, *grad_bias;
+    int *row_slot;
+    float lr, beta1, beta2, eps, beta1_power, beta2_power;
+    unsigned long long *sync_words;    // [0] ready (steps whose gradient is published), [1] done (CTA arrivals)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void add_release(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(GRAD_THREADS, 1) train_loop_kernel(const __grid_constant__ LoopArgs a) {
+    extern __shared__ int smem[];
+    unsigned long long *ready = a.sync_words, *done = a.sync_words + 1;
+    float b1p = a.beta1_power, b2p = a.beta2_power;
+    for (long long s = 0; s < a.n_starts; ++s) {
+        if (blockIdx.x == 0) {
+            const long long start = a.starts[s];
+            const long long end = start + a.batch_size < a.n_rows ? start + a.batch_size : a.n_rows;
+            pair_grad_body<true>(smem, a.mode, (int)(end - start), (int)(end - start), a.node_id + start, a.node_neighbor_id + start,
+                                 a.aux + start, a.emb, a.bias, a.ld, a.lambda, a.n_unique, a.uniq_ids, a.grad_rows, a.grad_bias,
+                                 a.row_slot);
+            __syncthreads();
+            if (threadIdx.x == 0) st_release(ready, (unsigned long long)(s + 1));
+        } else {
+            if (threadIdx.x == 0) while (ld_acquire(ready) < (unsigned long long)(s + 1)) {}
+            __syncthreads();
+        }
+        // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t): the same fp32 operation sequence as the host loop
+        const float lr_t = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+        adam_rows<true>(a.n_node, a.ld, a.emb, a.m_emb, a.v_emb, a.bias, a.m_bias, a.v_bias, a.grad_rows, a.grad_bias,
+                        a.row_slot, lr_t, a.beta1, a.beta2, a.eps);
+        b1p = __fmul_rn(b1p, a.beta1);
+        b2p = __fmul_rn(b2p, a.beta2);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            add_release(done, 1ull);
+            if (blockIdx.x == 0) while (ld_acquire(done) < (unsigned long long)gridDim.x * (unsigned long long)(s + 1)) {}
+        }
+        if (blockIdx.x == 0) __syncthreads();
+    }
+}
+}  // namespace
+}  // namespace gg
+
+extern "C" int gg_train_loop(int32_t mode, int64_t n_rows, const int64_t *start_list_dev, int64_t n_starts, int32_t batch_size,
+                             const int32_t *node_id, const int32_t *node_neighbor_id, const float *aux, int64_t n_node,
+                             int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias, float *v_bias,
+                             float lambda, int32_t *n_unique, int32_t *uniq_ids, float *grad_rows, float *grad_bias,
+                             int32_t *row_slot, float lr, float beta1, float beta2, float eps, float *beta1_power,
+                             float *beta2_power, uint64_t *sync_words, void *stream) {
+    GG_REQUIRE(start_list_dev && beta1_power && beta2_power && sync_words, "null pointer");
+    GG_REQUIRE(batch_size > 0 && batch_size <= GG_MAX_BATCH, "batch size out of range");
+    GG_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (discriminator) or 1 (generator)");
+    GG_REQUIRE(ld > 0 && ld % 32 == 0, "ld must be a positive multiple of 32");
+    if (n_starts == 0) return 0;
+    int dev = 0, coop = 0, per_sm = 0;
+    GG_CHECK(cudaGetDevice(&dev));
+    GG_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GG_REQUIRE(coop, "device does not support cooperative launches");
+    const size_t smem = (size_t)batch_size * 5 * 4;
+    GG_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gg::train_loop_kernel, gg::GRAD_THREADS, smem));
+    GG_REQUIRE(per_sm >= 1, "step loop kernel does not fit on an SM");
+    // enough CTAs to give every warp ~2 rows of the sweep, at most one per SM (small graphs: fewer CTAs, cheaper barrier)
+    long long ctas = (n_node + 63) / 64;
+    if (ctas > gg::sm_count()) ctas = gg::sm_count();
+    if (ctas < 1) ctas = 1;
+    gg::LoopArgs a;
+    a.mode = mode; a.batch_size = batch_size; a.ld = ld; a.n_rows = n_rows; a.n_starts = n_starts; a.n_node = n_node;
+    a.starts = (const long long *)start_list_dev; a.node_id = node_id; a.node_neighbor_id = node_neighbor_id; a.aux = aux;
+    a.emb = emb; a.m_emb = m_emb; a.v_emb = v_emb; a.bias = bias; a.m_bias = m_bias; a.v_bias = v_bias; a.lambda = lambda;
+    a.n_unique = n_unique; a.uniq_ids = uniq_ids; a.grad_rows = grad_rows; a.grad_bias = grad_bias; a.row_slot = row_slot;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.beta1_power = *beta1_power; a.beta2_power = *beta2_power;
+    a.sync_words = (unsigned long long *)sync_words;
+    GG_CHECK(cudaMemsetAsync(sync_words, 0, 2 * sizeof(uint64_t), (cudaStream_t)stream));
+    void *args[] = {&a};
+    GG_CHECK(cudaLaunchCooperativeKernel((const void *)gg::train_loop_kernel, dim3((unsigned)ctas), dim3(gg::GRAD_THREADS), args,
+                                         smem, (cudaStream_t)stream));
+    // the accumulators advance deterministically: replay the fp32 products on the host
+    for (int64_t s = 0; s < n_starts; ++s) {
         volatile float p1 = *beta1_power * beta1, p2 = *beta2_power * beta2;
         *beta1_power = p1;
         *beta2_power = p2;

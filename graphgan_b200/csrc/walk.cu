@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_kernel(const __gri
         unsigned int wi = 0;
         if (lane == 0) wi = atomicAdd(d.work_counter, 1u);
         wi = __shfl_sync(FULL, wi, 0);
-        const long long w = wi;
-        if (w >= d.n_walks) break;
+        if ((long long)wi >= d.n_walks) break;
+        const long long w = d.walk_order ? (long long)__ldg(d.walk_order + wi) : (long long)wi;
         // walk -> root slot: last slot with walk_ptr[slot] <= w (table when the caller provides one)
         int slot;
         if (d.walk_slot) {

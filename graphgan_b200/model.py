@@ -53,6 +53,7 @@ class PairModel:
         self.row_slot = torch.full((n_node,), -1, dtype=torch.int32, device=dev)
         self.uniq_ids = torch.zeros(2 * MAX_BATCH, dtype=torch.int32, device=dev)
         self.n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.sync_words = torch.zeros(2, dtype=torch.int64, device=dev)     # ready flag + arrival counter of gg_train_loop
         self.grad_rows = z(2 * MAX_BATCH, self.ld)
         self.grad_bias = z(2 * MAX_BATCH)
         # tf.train.AdamOptimizer defaults
@@ -98,7 +99,7 @@ class PairModel:
                     "gg_pair_grad")
         self.apply_adam()
 
-    def train_steps(self, node_id, node_neighbor_id, aux, start_list, batch_size):
+    def train_steps(self, node_id, node_neighbor_id, aux, start_list, batch_size, persistent=False):
         """All optimizer steps of one inner epoch (graph_gan.py:149-157 / 168-176): ``start_list`` is the shuffled
         list of batch starts; rows come from the device arrays.  Identical to calling ``step`` per batch."""
         i, j, a = self._dev_i32(node_id), self._dev_i32(node_neighbor_id), self._dev_f32(aux)
@@ -108,6 +109,19 @@ class PairModel:
         if batch_size > MAX_BATCH:
             raise ValueError("batch of %d pairs exceeds GG_MAX_BATCH=%d" % (batch_size, MAX_BATCH))
         b1p, b2p = C.c_float(float(self.beta1_power)), C.c_float(float(self.beta2_power))
+        if persistent:   # one cooperative launch for the whole start list (csrc/steps.cu: train_loop_kernel)
+            starts_d = self.torch.as_tensor(starts).to(self.device)
+            _cabi.check(self.lib.gg_train_loop(self._step_mode, int(i.shape[0]), ptr(starts_d), int(starts.size),
+                                               int(batch_size), ptr(i), ptr(j), ptr(a), self.n_node, self.ld, ptr(self.emb),
+                                               ptr(self.m_emb), ptr(self.v_emb), ptr(self.bias_t), ptr(self.m_bias), ptr(self.v_bias),
+                                               C.c_float(float(self.lam)), ptr(self.n_unique), ptr(self.uniq_ids), ptr(self.grad_rows),
+                                               ptr(self.grad_bias), ptr(self.row_slot), C.c_float(float(self.lr)),
+                                               C.c_float(float(self.beta1)), C.c_float(float(self.beta2)), C.c_float(float(self.eps)),
+                                               C.byref(b1p), C.byref(b2p), ptr(self.sync_words), self._stream()), "gg_train_loop")
+            self._keep = (starts_d, i, j, a)     # keep the device arrays alive until the stream has consumed them
+            self.beta1_power, self.beta2_power = np.float32(b1p.value), np.float32(b2p.value)
+            self.step_count += int(starts.size)
+            return
         _cabi.check(self.lib.gg_train_steps(self._step_mode, int(i.shape[0]), starts.ctypes.data_as(C.c_void_p), int(starts.size),
                                             int(batch_size), ptr(i), ptr(j), ptr(a), self.n_node, self.ld, ptr(self.emb),
                                             ptr(self.m_emb), ptr(self.v_emb), ptr(self.bias_t), ptr(self.m_bias), ptr(self.v_bias),

@@ -88,6 +88,7 @@ class WalkPlan:
         self.root_q = torch.empty(nq, dtype=torch.float64, device=dev)
         self.root_sc = torch.empty(nq, dtype=torch.float32, device=dev)
         self._s1 = None
+        self._order = None
         W = max(self.n_walks, 1)
         i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
         self.samples, self.status, self.first_edge, self.wsteps, self.wsuml = i32(W), i32(W), i32(W), i32(W), i32(W)
@@ -99,6 +100,26 @@ class WalkPlan:
         self.n_rows = torch.zeros(1, dtype=torch.int64, device=dev)
         self.rows = [i32(max(2 * self.n_walks, 1)) for _ in range(3)] if for_d else None
 
+
+    def start_order(self, sampler):
+        """Order in which walk_kernel starts the walks: roots whose neighbourhood holds the largest hub first
+        (a walk that steps onto a 10 k-neighbour node costs ~100x a median one; started last it would be the
+        tail of the launch), walks of one root kept together (they share the parent array in L2).  Static per
+        plan; plumbing only (one gather, one segment max, one sort)."""
+        if self._order is None and self.n_walks > 0 and self.nq > 0:
+            torch, g, dev = sampler.torch, sampler.g, sampler.device
+            R = self.n_roots
+            deg_r = self.rq_ptr[1:] - self.rq_ptr[:-1]
+            slot = torch.repeat_interleave(torch.arange(R, dtype=torch.int64, device=dev), deg_r, output_size=self.nq)
+            ent = g.indptr[self.trees.roots.long()[slot]] + (torch.arange(self.nq, dtype=torch.int64, device=dev) - self.rq_ptr[slot])
+            c = g.adj[ent].long()
+            key = torch.zeros(R, dtype=torch.int64, device=dev).scatter_reduce_(0, slot, g.indptr[c + 1] - g.indptr[c], "amax")
+            perm = torch.argsort(key, descending=True, stable=True)
+            nw = (self.walk_ptr[1:] - self.walk_ptr[:-1])[perm]
+            first = torch.cumsum(nw, 0) - nw                                  # position of each root's first walk in the order
+            base = torch.repeat_interleave(self.walk_ptr[:-1][perm] - first, nw, output_size=self.n_walks)
+            self._order = (base + torch.arange(self.n_walks, dtype=torch.int64, device=dev)).to(torch.int32)
+        return self._order
 
     def depth1_buffers(self, sampler):
         """Static layout of the depth-1 CDF cache (csrc/walk.cu: step1_cdf_kernel): one slice of degree(child) + 1
@@ -120,7 +141,7 @@ class WalkPlan:
 
 
 class WalkSampler:
-    def __init__(self, graph, hub_threshold=256, algo="walk", chunk_walks=8, depth1=False):
+    def __init__(self, graph, hub_threshold=256, algo="walk", chunk_walks=8, depth1=False, hub_first=True):
         import torch
         self.torch = torch
         self.g = graph
@@ -137,6 +158,7 @@ class WalkSampler:
         # kernel (1.79 -> 1.08 ms) but the kernel that builds the CDFs takes 1.39 ms, because a 13.8k-entry hub list
         # is built by a single warp (~1 ms) -- it needs a CTA-cooperative path for giant lists first
         self.depth1 = bool(depth1)
+        self.hub_first = bool(hub_first)          # start order of the walks (WalkPlan.start_order); results do not depend on it
         nbytes = C.c_int64(0)
         _cabi.check(self.lib.gg_walk_scratch_bytes(self.max_cand, C.byref(nbytes)), "gg_walk_scratch_bytes")
         self.scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
@@ -181,6 +203,8 @@ class WalkSampler:
         d.paths, d.path_len, d.counters = ptr(plan.paths), ptr(plan.path_len), ptr(plan.counters)
         d.scratch, d.scratch_bytes, d.work_counter = ptr(self.scratch), self.scratch.numel(), ptr(self.work_counter)
         d.rq_ptr, d.walk_slot = ptr(plan.rq_ptr), ptr(plan.walk_slot)
+        if self.hub_first and rng_mode == RNG_PHILOX and self.algo == "walk":
+            d.walk_order = ptr(plan.start_order(self))
         if self.algo == "chunk" and rng_mode == RNG_PHILOX:
             d.chunk_ptr, d.n_chunks, d.chunk_walks = ptr(plan.chunk_ptr), plan.n_chunks, self.chunk_walks
         if reuse:

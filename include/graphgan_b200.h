@@ -121,6 +121,8 @@ typedef struct gg_walk_desc {
     double *s1_q;               /* device pool [s1_ptr[s1_nq]]: normalised CDFs */
     int32_t *s1_ids;            /* device pool: candidate ids */
     int32_t *first_idx;         /* device [W] scratch: root-step choice of every walk */
+    const int32_t *walk_order;  /* optional device [W]: the order in which walk_kernel starts the walks (a permutation of
+                                 * 0..W-1, e.g. expensive roots first); results do not depend on it (Philox mode) */
 } gg_walk_desc;
 
 /* all_score[u, v] = e_u.e_v + b_v (generator.py:21) for every walk-CSR entry (u -> v) of the listed hub
@@ -214,6 +216,16 @@ int gg_train_steps(int32_t mode, int64_t n_rows, const int64_t *start_list, int6
                    float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias, float *v_bias, float lambda,
                    int32_t *n_unique, int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot, float lr,
                    float beta1, float beta2, float eps, float *beta1_power, float *beta2_power, void *stream);
+
+/* The same loop as gg_train_steps in ONE cooperative launch (persistent kernel; a ready flag and an arrival
+ * counter order the gradient and the Adam sweep of every step).  start_list_dev is a DEVICE array; sync_words
+ * is a device scratch of two uint64 (zeroed by the call).  Bit-identical results. */
+int gg_train_loop(int32_t mode, int64_t n_rows, const int64_t *start_list_dev, int64_t n_starts, int32_t batch_size,
+                  const int32_t *node_id, const int32_t *node_neighbor_id, const float *aux, int64_t n_node, int32_t ld,
+                  float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias, float *v_bias, float lambda,
+                  int32_t *n_unique, int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot, float lr,
+                  float beta1, float beta2, float eps, float *beta1_power, float *beta2_power, uint64_t *sync_words,
+                  void *stream);
 
 /* get_node_pairs_from_path (graph_gan.py:272-291) for a batch of recorded paths.
  * pair_ptr: device [W+1] (out, exclusive scan of per-path pair counts). */

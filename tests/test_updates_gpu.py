@@ -243,7 +243,11 @@ def test_train_steps_equals_step_by_step(cuda_device):
         a, b = cls(n, emb, device=cuda_device), cls(n, emb, device=cuda_device)
         for s0 in starts:
             a.step(i[s0:s0 + B], j[s0:s0 + B], aux[s0:s0 + B])
-        b.train_steps(i, j, aux, starts, B)
+        b.train_steps(i, j, aux, starts, B, persistent=False)
+        c = cls(n, emb, device=cuda_device)
+        c.train_steps(i, j, aux, starts, B, persistent=True)      # one cooperative launch (train_loop_kernel)
+        assert torch.equal(a.emb, c.emb) and torch.equal(a.bias_t, c.bias_t) and torch.equal(a.m_emb, c.m_emb)
+        assert a.beta1_power == c.beta1_power and a.step_count == c.step_count and int((c.row_slot != -1).sum()) == 0
         assert torch.equal(a.emb, b.emb) and torch.equal(a.bias_t, b.bias_t) and torch.equal(a.v_emb, b.v_emb)
         assert a.beta1_power == b.beta1_power and a.beta2_power == b.beta2_power and a.step_count == b.step_count
         assert float(a.lr_t()) == float(b.lr_t())

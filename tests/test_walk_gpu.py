@@ -133,6 +133,12 @@ def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, 
     gp, rp = out_g.paths.cpu().numpy(), ref_g.paths
     for w in np.flatnonzero(ref_g.status == can.DONE):
         assert np.array_equal(gp[w, :ref_g.path_len[w]], rp[w, :ref_g.path_len[w]])
+    if algo == "walk":   # the start order of the walks (WalkPlan.start_order) must not change anything
+        assert smp.hub_first
+        smp.hub_first = False
+        out2 = smp.run(emb, bias, trees, sn, True, seed=seed, pass_tag=3, update_ratio=update_ratio)
+        for name in ("samples", "status", "wsteps", "wsuml", "root_ok", "first_edge"):
+            assert torch.equal(getattr(out2, name), getattr(out, name)), name
     cg = out_g.counters_host()
     assert (cg["steps"], cg["sum_l"]) == (ref_g.steps, ref_g.sum_l)
     return cnt, cg
