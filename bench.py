@@ -41,15 +41,18 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="powerlaw_1m", choices=sorted(WORKLOADS))
-    p.add_argument("--roots", type=int, default=4096, help="resident roots per GPU (R)")
+    p.add_argument("--roots", type=int, default=16384,
+                   help="resident roots per GPU (R); the parent arrays take 4*N*R bytes (64 GB at N = 1M), capped at "
+                        "half of the device memory")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--hub-threshold", type=int, default=256, help="degree from which adjacency scores are cached per pass")
+    p.add_argument("--hub-threshold", type=int, default=128, help="degree from which adjacency scores are cached per pass")
     p.add_argument("--algo", default="walk", choices=["chunk", "walk"], help="order-free walk kernel")
     p.add_argument("--chunk-walks", type=int, default=8, help="walks per chunk for --algo chunk")
     p.add_argument("--file-order", action="store_true", help="start the walks in root order instead of hub-neighbourhoods first")
-    p.add_argument("--depth1", action="store_true", help="enable the per-(root, depth-1 child) CDF reuse (experimental)")
+    p.add_argument("--no-depth1", dest="depth1", action="store_false",
+                   help="disable the per-(root, depth-1 child) CDF reuse (csrc/walk.cu: step1_cdf_kernel)")
     return p.parse_args()
 
 
@@ -70,7 +73,13 @@ def make_inputs(args, rank):
             pass
     hg = G.HostGraph(edges, None, n_node=n)
     emb = synth.embeddings(n, d, seed=args.seed + 1)
-    roots = synth.pick_roots(hg.degrees(), args.roots, seed=args.seed + 101 * rank)
+    n_roots = args.roots
+    if args.impl == "b200":      # "R chosen so parent[R, N] fits"
+        import torch
+        total = torch.cuda.mem_get_info()[1]
+        n_roots = max(1, min(n_roots, int(total // 2 // (4 * n))))
+        args.roots = n_roots
+    roots = synth.pick_roots(hg.degrees(), n_roots, seed=args.seed + 101 * rank)
     return hg, emb, roots, d
 
 

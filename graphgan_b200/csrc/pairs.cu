@@ -225,7 +225,7 @@ extern "C" int gg_pair_grad(int32_t mode, int32_t n_pairs, int32_t batch_total, 
     GG_REQUIRE(node_id && node_neighbor_id && aux && emb && bias && n_unique && uniq_ids && grad_rows && grad_bias && row_slot,
                "null pointer");
     GG_REQUIRE(ld > 0 && ld % 32 == 0, "ld must be a positive multiple of 32");
-    const size_t smem = (size_t)n_pairs * (2 + 2 + 1) * 4;
+    const size_t smem = gg::pair_grad_smem_bytes(n_pairs);
     gg::pair_grad_kernel<<<1, gg::GRAD_THREADS, smem, (cudaStream_t)stream>>>(
         mode, n_pairs, batch_total > 0 ? batch_total : n_pairs, node_id, node_neighbor_id, aux, emb, bias, ld, lambda,
         n_unique, uniq_ids, grad_rows, grad_bias, row_slot);

@@ -61,7 +61,8 @@ struct LoopArgs {
     float *grad_rows, *grad_bias;
     int *row_slot;
     float lr, beta1, beta2, eps, beta1_power, beta2_power;
-    unsigned long long *sync_words;    // [0] ready (steps whose gradient is published), [1] done (CTA arrivals)
+    unsigned long long *sync_words;    // [0] ready (steps whose gradient is published), [1] done (CTA arrivals),
+                                       // [2..5] CTA 0's cycles in gradient / sweep / wait and the step count (diagnostic)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
@@ -76,35 +77,46 @@ __device__ __forceinline__ void add_release(unsigned long long *p, unsigned long
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(GRAD_THREADS, 1) train_loop_kernel(const __grid_constant__ LoopArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) train_loop_kernel(const __grid_constant__ LoopArgs a) {
     extern __shared__ int smem[];
     unsigned long long *ready = a.sync_words, *done = a.sync_words + 1;
     float b1p = a.beta1_power, b2p = a.beta2_power;
+    const bool clk = blockIdx.x == 0 && threadIdx.x == 0;     // CTA 0 keeps a cycle breakdown (diagnostic)
+    long long c_grad = 0, c_sweep = 0, c_wait = 0;
     for (long long s = 0; s < a.n_starts; ++s) {
+        const long long t0 = clk ? clock64() : 0;
         if (blockIdx.x == 0) {
             const long long start = a.starts[s];
             const long long end = start + a.batch_size < a.n_rows ? start + a.batch_size : a.n_rows;
-            pair_grad_body<true>(smem, a.mode, (int)(end - start), (int)(end - start), a.node_id + start, a.node_neighbor_id + start,
-                                 a.aux + start, a.emb, a.bias, a.ld, a.lambda, a.n_unique, a.uniq_ids, a.grad_rows, a.grad_bias,
-                                 a.row_slot);
+            pair_grad_body<true, NT>(smem, a.mode, (int)(end - start), (int)(end - start), a.node_id + start, a.node_neighbor_id + start,
+                                     a.aux + start, a.emb, a.bias, a.ld, a.lambda, a.n_unique, a.uniq_ids, a.grad_rows, a.grad_bias,
+                                     a.row_slot);
             __syncthreads();
             if (threadIdx.x == 0) st_release(ready, (unsigned long long)(s + 1));
         } else {
             if (threadIdx.x == 0) while (ld_acquire(ready) < (unsigned long long)(s + 1)) {}
             __syncthreads();
         }
+        const long long t1 = clk ? clock64() : 0;
         // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t): the same fp32 operation sequence as the host loop
         const float lr_t = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
-        adam_rows<true>(a.n_node, a.ld, a.emb, a.m_emb, a.v_emb, a.bias, a.m_bias, a.v_bias, a.grad_rows, a.grad_bias,
-                        a.row_slot, lr_t, a.beta1, a.beta2, a.eps);
+        adam_rows<true, 2, false>(a.n_node, a.ld, a.emb, a.m_emb, a.v_emb, a.bias, a.m_bias, a.v_bias, a.grad_rows, a.grad_bias,
+                                  a.row_slot, lr_t, a.beta1, a.beta2, a.eps);
         b1p = __fmul_rn(b1p, a.beta1);
         b2p = __fmul_rn(b2p, a.beta2);
         __syncthreads();
+        const long long t2 = clk ? clock64() : 0;
         if (threadIdx.x == 0) {
             add_release(done, 1ull);
             if (blockIdx.x == 0) while (ld_acquire(done) < (unsigned long long)gridDim.x * (unsigned long long)(s + 1)) {}
         }
         if (blockIdx.x == 0) __syncthreads();
+        if (clk) { c_grad += t1 - t0; c_sweep += t2 - t1; c_wait += clock64() - t2; }
+    }
+    if (clk) {
+        a.sync_words[2] = (unsigned long long)c_grad; a.sync_words[3] = (unsigned long long)c_sweep;
+        a.sync_words[4] = (unsigned long long)c_wait; a.sync_words[5] = (unsigned long long)a.n_starts;
     }
 }
 }  // namespace
@@ -125,10 +137,13 @@ extern "C" int gg_train_loop(int32_t mode, int64_t n_rows, const int64_t *start_
     GG_CHECK(cudaGetDevice(&dev));
     GG_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     GG_REQUIRE(coop, "device does not support cooperative launches");
-    const size_t smem = (size_t)batch_size * 5 * 4;
-    GG_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gg::train_loop_kernel, gg::GRAD_THREADS, smem));
+    const size_t smem = gg::pair_grad_smem_bytes(batch_size);
+    // 512 threads: the 64-register ceiling of a 1024-thread CTA makes the fused body spill (measured 18.7 vs 13.5 us/step)
+    constexpr int NT = 512;
+    const void *kern = (const void *)gg::train_loop_kernel<NT>;
+    GG_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gg::train_loop_kernel<NT>, NT, smem));
     GG_REQUIRE(per_sm >= 1, "step loop kernel does not fit on an SM");
-    // enough CTAs to give every warp ~2 rows of the sweep, at most one per SM (small graphs: fewer CTAs, cheaper barrier)
+    // one sweep iteration per warp (2 segments of 512 B in flight), at most one CTA per SM
     long long ctas = (n_node + 63) / 64;
     if (ctas > gg::sm_count()) ctas = gg::sm_count();
     if (ctas < 1) ctas = 1;
@@ -139,9 +154,9 @@ extern "C" int gg_train_loop(int32_t mode, int64_t n_rows, const int64_t *start_
     a.n_unique = n_unique; a.uniq_ids = uniq_ids; a.grad_rows = grad_rows; a.grad_bias = grad_bias; a.row_slot = row_slot;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.beta1_power = *beta1_power; a.beta2_power = *beta2_power;
     a.sync_words = (unsigned long long *)sync_words;
-    GG_CHECK(cudaMemsetAsync(sync_words, 0, 2 * sizeof(uint64_t), (cudaStream_t)stream));
+    GG_CHECK(cudaMemsetAsync(sync_words, 0, 8 * sizeof(uint64_t), (cudaStream_t)stream));
     void *args[] = {&a};
-    GG_CHECK(cudaLaunchCooperativeKernel((const void *)gg::train_loop_kernel, dim3((unsigned)ctas), dim3(gg::GRAD_THREADS), args,
+    GG_CHECK(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3(NT), args,
                                          smem, (cudaStream_t)stream));
     // the accumulators advance deterministically: replay the fp32 products on the host
     for (int64_t s = 0; s < n_starts; ++s) {

@@ -109,6 +109,9 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t 
 }
 
 // One complete walk, executed by a full warp.  Returns the status.
+// a (root, depth-1 child) pair gets a shared CDF (step1_cdf_kernel) when at least this many walks picked it
+constexpr int S1_MIN_WALKS = 2;
+
 template <int CPL>
 __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slot, uint32_t k, long long w,
                                         int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
@@ -129,6 +132,11 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
         const long long a0 = d.indptr[cur], a1 = d.indptr[cur + 1];
         int n, idx, nxt;
         bool inc_father = false;
+        long long s1pos = -1;     // slice of the depth-1 cache, when this (root, child) pair was picked by >= 2 walks
+        if (step == 1 && d.s1_q) {
+            s1pos = __ldg(d.rq_ptr + slot) + (fedge - d.indptr[root]);
+            if (__ldg(d.s1_cnt + s1pos) < S1_MIN_WALKS) s1pos = -1;
+        }
         if (step == 0 && d.root_q) {
             // ---- root step from the per-root CDF (hub.cu: root_cdf_kernel): every walk of a root
             // sees the same candidate list tree[root][1:] and the same scores, so the softmax/CDF
@@ -139,16 +147,15 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             if (rng.exhausted) { status = GG_NOTRUN; break; }
             idx = d.first_idx ? __ldg(d.first_idx + w) : cdf_search(d.root_q + __ldg(d.rq_ptr + slot), n, u);
             nxt = __ldg(d.adj + a0 + idx);
-        } else if (step == 1 && d.s1_q) {
+        } else if (s1pos >= 0) {
             // ---- depth-1 step from the per-(root, child) CDF (step1_cdf_kernel): walks of a root that picked the
             // same child share one candidate list; it was built once, each walk only inverts it
-            const long long pos = __ldg(d.rq_ptr + slot) + (fedge - d.indptr[root]);
-            n = __ldg(d.s1_n + pos);
+            n = __ldg(d.s1_n + s1pos);
             if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:255-257
             inc_father = !d.for_d && !((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u);
             const double u = rng.draw((uint32_t)root, k, 1u);
-            const long long o = __ldg(d.s1_ptr + pos);
-            idx = (n == 1) ? 0 : cdf_search(d.s1_q + o, n, u);
+            const long long o = __ldg(d.s1_ptr + s1pos);
+            idx = (n == 1) ? 0 : cdf_search_raw(d.s1_q + o, n, u);
             nxt = __ldg(d.s1_ids + o + idx);
         } else {
             // ---- candidate list (graph_gan.py:250-259) + scores
@@ -216,6 +223,8 @@ __global__ void root_step_kernel(const __grid_constant__ gg_walk_desc d) {
     atomicAdd(d.s1_cnt + o + idx, 1);
 }
 
+constexpr int S1_SINGLES = 8192, S1_CHUNK = 16;
+
 template <int CPL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) step1_cdf_kernel(const __grid_constant__ gg_walk_desc d) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
@@ -228,8 +237,31 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) step1_cdf_kernel(const 
     float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
     unsigned long long rows_gathered = 0;
     unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (long long pos = gw; pos < d.s1_nq; pos += nwarps) {
-        if (__ldg(d.s1_cnt + pos) == 0) continue;
+    // queue mode (s1_order): the first S1_SINGLES items are single pairs (the largest lists, one warp each, started
+    // first); after them one item is a chunk of S1_CHUNK pairs (most pairs were never picked: one atomic per
+    // chunk keeps the queue cheap).  Without s1_order: static striding.
+    long long item = gw, sub = 0, sub_end = 0;
+    const long long n_single = d.s1_nq < S1_SINGLES ? d.s1_nq : S1_SINGLES;
+    const long long n_items = n_single + (d.s1_nq - n_single + S1_CHUNK - 1) / S1_CHUNK;
+    for (;;) {
+        long long pos;
+        if (d.s1_order) {
+            if (sub >= sub_end) {
+                unsigned int it = 0;
+                if (lane == 0) it = atomicAdd(d.work_counter, 1u);
+                it = __shfl_sync(FULL, it, 0);
+                if ((long long)it >= n_items) break;
+                if ((long long)it < n_single) { sub = it; sub_end = sub + 1; }
+                else { sub = n_single + ((long long)it - n_single) * S1_CHUNK; sub_end = sub + S1_CHUNK < d.s1_nq ? sub + S1_CHUNK : d.s1_nq; }
+            }
+            pos = __ldg(d.s1_order + sub);
+            ++sub;
+        } else {
+            if (item >= d.s1_nq) break;
+            pos = item;
+            item += nwarps;
+        }
+        if (__ldg(d.s1_cnt + pos) < S1_MIN_WALKS) continue;   // a pair picked once is cheaper inside its walk (no CDF array)
         const int slot = __ldg(d.s1_slot + pos);
         const int root = d.roots[slot];
         const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
@@ -242,8 +274,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) step1_cdf_kernel(const 
         if (n == 0) continue;
         const long long o = __ldg(d.s1_ptr + pos);
         for (int i = lane; i < n; i += 32) d.s1_ids[o + i] = ids[i];
-        if (n == 1) { if (lane == 0) d.s1_q[o] = 1.0; }
-        else cdf_store_m(sc, n, m, d.s1_q + o, lane);
+        if (n > 1) cdf_store_raw(sc, n, m, d.s1_q + o, lane);
         __syncwarp();
     }
     if (lane == 0 && rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
@@ -632,6 +663,7 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
             }
 #undef GG_S1
             GG_CHECK(cudaGetLastError());
+            GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));   // the walk kernel's queue starts at 0
         }
         if (d.chunk_ptr) {
             GG_REQUIRE(d.n_chunks >= 0 && d.n_chunks < (1ll << 32), "bad chunk count");

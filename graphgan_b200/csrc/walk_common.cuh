@@ -278,6 +278,42 @@ __device__ __forceinline__ void cdf_store(float *sc, int n, double *q_out, int l
     }
 }
 
+// un-normalised CDF c_i = carry + scan(e/S)_i written out, the total after the n entries (c[n] = total).  One scan
+// pass: the division by the total is left to the search, which performs it only on the entries it probes.
+__device__ __forceinline__ void cdf_store_raw(float *sc, int n, float m, double *c_out, int lane) {
+    const float S = softmax_exp_sum<false>(sc, n, m, lane);
+    double carry = 0.0;
+    for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
+        double x[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = t0 + 32 * u + lane;
+            x[u] = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;   // 0 / S == 0 for the padding lanes
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) x[u] = warp_scan_ks(x[u], lane);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (t0 + 32 * u >= n) break;               // warp-uniform
+            const int i = t0 + 32 * u + lane;
+            if (i < n) c_out[i] = __dadd_rn(carry, x[u]);
+            carry = __dadd_rn(carry, __shfl_sync(FULL, x[u], 31));
+        }
+    }
+    if (lane == 0) c_out[n] = carry;
+}
+
+// first i in [0,n) with c[i] / c[n] > u: the same comparison as cdf_pick / cdf_search, on the raw array
+__device__ __forceinline__ int cdf_search_raw(const double *__restrict__ c, int n, double u) {
+    const double total = __ldg(c + n);
+    int lo = 0, hi = n - 1;  // invariant: answer in [lo, hi]  (c[n-1] == total, so c[n-1] / total == 1 > u)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ddiv_rn(__ldg(c + mid), total) > u) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
 // first i in [0,n) with q[i] > u (q non-decreasing, q[n-1] == 1 > u): what the linear scan finds
 __device__ __forceinline__ int cdf_search(const double *__restrict__ q, int n, double u) {
     int lo = 0, hi = n - 1;  // invariant: answer in [lo, hi]

@@ -53,7 +53,7 @@ class PairModel:
         self.row_slot = torch.full((n_node,), -1, dtype=torch.int32, device=dev)
         self.uniq_ids = torch.zeros(2 * MAX_BATCH, dtype=torch.int32, device=dev)
         self.n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.sync_words = torch.zeros(2, dtype=torch.int64, device=dev)     # ready flag + arrival counter of gg_train_loop
+        self.sync_words = torch.zeros(8, dtype=torch.int64, device=dev)     # flag, counter, cycle breakdown of gg_train_loop
         self.grad_rows = z(2 * MAX_BATCH, self.ld)
         self.grad_bias = z(2 * MAX_BATCH)
         # tf.train.AdamOptimizer defaults
@@ -99,7 +99,7 @@ class PairModel:
                     "gg_pair_grad")
         self.apply_adam()
 
-    def train_steps(self, node_id, node_neighbor_id, aux, start_list, batch_size, persistent=False):
+    def train_steps(self, node_id, node_neighbor_id, aux, start_list, batch_size, persistent=None):
         """All optimizer steps of one inner epoch (graph_gan.py:149-157 / 168-176): ``start_list`` is the shuffled
         list of batch starts; rows come from the device arrays.  Identical to calling ``step`` per batch."""
         i, j, a = self._dev_i32(node_id), self._dev_i32(node_neighbor_id), self._dev_f32(aux)
@@ -109,6 +109,10 @@ class PairModel:
         if batch_size > MAX_BATCH:
             raise ValueError("batch of %d pairs exceeds GG_MAX_BATCH=%d" % (batch_size, MAX_BATCH))
         b1p, b2p = C.c_float(float(self.beta1_power)), C.c_float(float(self.beta2_power))
+        if persistent is None:
+            # the persistent loop wins while the dense sweep (E, m, v) stays in L2 (13.5 vs 18.7 us/step at C1); a sweep
+            # that streams from HBM is faster as its own full-occupancy launch (0.83 vs 1.0 ms/step at N = 1M, ld = 128)
+            persistent = 12 * self.n_node * self.ld <= (32 << 20)
         if persistent:   # one cooperative launch for the whole start list (csrc/steps.cu: train_loop_kernel)
             starts_d = self.torch.as_tensor(starts).to(self.device)
             _cabi.check(self.lib.gg_train_loop(self._step_mode, int(i.shape[0]), ptr(starts_d), int(starts.size),

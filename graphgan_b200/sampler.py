@@ -135,13 +135,14 @@ class WalkPlan:
             ptr_[1:] = torch.cumsum(g.indptr[c + 1] - g.indptr[c] + 1, 0)
             total = max(int(ptr_[-1].item()), 1)
             i32 = lambda k: torch.empty(max(k, 1), dtype=torch.int32, device=dev)
-            self._s1 = dict(slot=slot, ptr=ptr_, cnt=i32(self.nq), n=i32(self.nq), ids=i32(total),
+            order = torch.argsort(g.indptr[c + 1] - g.indptr[c], descending=True, stable=True).to(torch.int32)
+            self._s1 = dict(slot=slot, ptr=ptr_, cnt=i32(self.nq), n=i32(self.nq), ids=i32(total), order=order,
                             q=torch.empty(total, dtype=torch.float64, device=dev), first=i32(self.n_walks))
         return self._s1
 
 
 class WalkSampler:
-    def __init__(self, graph, hub_threshold=256, algo="walk", chunk_walks=8, depth1=False, hub_first=True):
+    def __init__(self, graph, hub_threshold=128, algo="walk", chunk_walks=8, depth1=True, hub_first=True):
         import torch
         self.torch = torch
         self.g = graph
@@ -154,9 +155,9 @@ class WalkSampler:
         assert algo in ("chunk", "walk")
         self.algo = algo
         self.chunk_walks = int(chunk_walks)
-        # one CDF per (root, depth-1 child) pair that occurs (needs reuse).  Off by default: on C3 it halves the walk
-        # kernel (1.79 -> 1.08 ms) but the kernel that builds the CDFs takes 1.39 ms, because a 13.8k-entry hub list
-        # is built by a single warp (~1 ms) -- it needs a CTA-cooperative path for giant lists first
+        # one CDF per (root, depth-1 child) pair that occurs (needs reuse): the walks of a root that pick the same child
+        # share its candidate list (5.5x fewer neighbour probes at step 1 on C3); the builder kernel pulls the pairs
+        # from a queue, largest lists first (hub_first), because a 13.8k-entry hub list occupies one warp for ~1 ms
         self.depth1 = bool(depth1)
         self.hub_first = bool(hub_first)          # start order of the walks (WalkPlan.start_order); results do not depend on it
         nbytes = C.c_int64(0)
@@ -214,6 +215,8 @@ class WalkSampler:
                 b = plan.depth1_buffers(self)
                 d.s1_nq, d.s1_slot, d.s1_ptr, d.s1_cnt, d.s1_n = plan.nq, ptr(b["slot"]), ptr(b["ptr"]), ptr(b["cnt"]), ptr(b["n"])
                 d.s1_q, d.s1_ids, d.first_idx = ptr(b["q"]), ptr(b["ids"]), ptr(b["first"])
+                if self.hub_first:
+                    d.s1_order = ptr(b["order"])
         return d
 
     def precompute(self, emb, bias, plan, desc=None):

@@ -121,6 +121,8 @@ typedef struct gg_walk_desc {
     double *s1_q;               /* device pool [s1_ptr[s1_nq]]: normalised CDFs */
     int32_t *s1_ids;            /* device pool: candidate ids */
     int32_t *first_idx;         /* device [W] scratch: root-step choice of every walk */
+    const int32_t *s1_order;    /* optional device [s1_nq]: the (root, child) pairs sorted by decreasing child degree; with it
+                                 * step1_cdf_kernel pulls pairs from a queue (largest lists first) instead of striding */
     const int32_t *walk_order;  /* optional device [W]: the order in which walk_kernel starts the walks (a permutation of
                                  * 0..W-1, e.g. expensive roots first); results do not depend on it (Philox mode) */
 } gg_walk_desc;
@@ -219,7 +221,8 @@ int gg_train_steps(int32_t mode, int64_t n_rows, const int64_t *start_list, int6
 
 /* The same loop as gg_train_steps in ONE cooperative launch (persistent kernel; a ready flag and an arrival
  * counter order the gradient and the Adam sweep of every step).  start_list_dev is a DEVICE array; sync_words
- * is a device scratch of two uint64 (zeroed by the call).  Bit-identical results. */
+ * is a device scratch of eight uint64 (zeroed by the call; [0..1] flag and counter, [2..5] diagnostic: CTA 0's
+ * clock cycles in gradient / sweep / wait, and the number of steps).  Bit-identical results. */
 int gg_train_loop(int32_t mode, int64_t n_rows, const int64_t *start_list_dev, int64_t n_starts, int32_t batch_size,
                   const int32_t *node_id, const int32_t *node_neighbor_id, const float *aux, int64_t n_node, int32_t ld,
                   float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias, float *v_bias, float lambda,

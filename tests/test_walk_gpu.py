@@ -11,7 +11,7 @@ from tests.golden import loader
 pytestmark = pytest.mark.gpu
 
 
-def _setup(case, cuda_device, roots=None, hub_threshold=256, algo="chunk", chunk_walks=32, depth1=True):
+def _setup(case, cuda_device, roots=None, hub_threshold=256, algo="walk", chunk_walks=32, depth1=True):
     import torch
     from graphgan_b200 import graph as G, sampler as S
     from oracle import canonical as can
@@ -95,11 +95,12 @@ def test_stream_replay_matches_reference(name, hub, cuda_device):
         assert got[k] == pf[pp[k]:pp[k + 1]].tolist()
 
 
-def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256, algo="chunk", chunk_walks=32):
+def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256, algo="walk", chunk_walks=32,
+                    depth1=True):
     import torch
     from graphgan_b200 import sampler as S
     from oracle import canonical as can
-    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold, algo, chunk_walks)
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold, algo, chunk_walks, depth1)
     par = trees.parent.cpu().numpy()
     E = can.pad_rows(case.emb_g)
     bits = np.zeros(dg.n_bit_words, np.uint32)
@@ -154,14 +155,14 @@ def test_philox_matches_canonical_oracle(name, ratio, hub, cuda_device):
                     hub_threshold=hub)
 
 
-@pytest.mark.parametrize("algo", ["walk", "chunk"])
+@pytest.mark.parametrize("algo,depth1", [("walk", False), ("chunk", True)])
 @pytest.mark.parametrize("name,hub,ratio", [("rand300", 0, 0.6), ("rand1200", 256, 1.0), ("cagrqc", 8, 1.0)])
-def test_philox_other_kernels(name, hub, ratio, algo, cuda_device):
-    """Both order-free kernels (one warp per walk -- the default -- and one warp per chunk of walks, here with
-    a ragged chunk size) agree bit for bit."""
+def test_philox_other_kernels(name, hub, ratio, algo, depth1, cuda_device):
+    """The non-default order-free paths -- one warp per walk WITHOUT the depth-1 CDF reuse, and one warp per chunk
+    of walks (here with a ragged chunk size) -- agree bit for bit with the oracle (and so with the default path)."""
     case = loader.load(name)
     _philox_compare(case, cuda_device, None, ratio, seed=4242, n_sample_gen=int(case.n_sample_gen), hub_threshold=hub,
-                    algo=algo, chunk_walks=5)
+                    algo=algo, chunk_walks=5, depth1=depth1)
 
 
 @pytest.mark.parametrize("hub", [0, 64, 256])

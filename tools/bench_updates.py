@@ -33,13 +33,26 @@ def main():
     r = torch.as_tensor(rng.random(P).astype(np.float32)).cuda()
     starts = (rng.integers(0, P // B, S) * B).astype(np.int64)
     res = {}
-    for persistent in (False, True):
+    import os
+    variants = [(False, None, None), (True, None, None)]
+    for persistent, nt, ct in variants:
+        for k, val in (("GG_LOOP_THREADS", nt), ("GG_LOOP_CTAS", ct)):
+            if val is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(val)
         g = Generator(n, init)
         g.train_steps(i, j, r, starts[:64], B, persistent=persistent)          # warm-up
         us = timed(lambda: g.train_steps(i, j, r, starts, B, persistent=persistent))
-        res[persistent] = g.emb.clone()
-        print("%-15s %8.2f us/step  (%d steps, n=%d ld=%d B=%d)" % ("gg_train_loop" if persistent else "gg_train_steps",
-                                                                     us / S, S, n, g.ld, B))
+        if persistent not in res:
+            res[persistent] = g.emb.clone()
+        else:
+            assert torch.equal(res[persistent], g.emb)
+        print("%-15s %8.2f us/step  (%d steps, n=%d ld=%d B=%d)" % ("gg_train_loop" if persistent else "gg_train_steps", us / S, S, n, g.ld, B))
+        if persistent:
+            c = g.sync_words.cpu().numpy()
+            print("   CTA 0 cycles per step: gradient %.0f, sweep %.0f, wait for the other CTAs %.0f" % tuple(c[2:5] / max(c[5], 1)))
+    os.environ.pop("GG_LOOP_THREADS", None); os.environ.pop("GG_LOOP_CTAS", None)
     print("bit-identical:", bool(torch.equal(res[False], res[True])))
     g = Generator(n, init)
     lib = g.lib
