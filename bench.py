@@ -413,7 +413,8 @@ def run_b200(args):
             "gpu_launches": ((9 if smp.depth1 and args.algo == "walk" else 7) if reuse else 5) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "K1 stage: gg::hub_score_kernel + gg::root_cdf_kernel + gg::walk_kernel (ld=%d)" % ld,
+                         "kernel": "K1 stage: gg::hub_score_kernel + gg::root_cdf_kernel + gg_walk_sample (%sgg::walk_kernel) (ld=%d)" % (
+                             "gg::root_step_kernel + gg::step1_cdf_kernel + " if smp.depth1 and args.algo == "walk" else "", ld),
                          "kernel_ms": k_ms, "precompute_ms": pre_ms, "walk_kernel_ms": walk_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "bytes_per_neg_edge": alg_bytes / max(c0["accepted"], 1),
@@ -421,9 +422,10 @@ def run_b200(args):
                          "executed_achieved": exec_bytes / (k_ms * 1e-3) / 1e9,
                          "executed_frac": exec_bytes / (k_ms * 1e-3) / 1e9 / peak,
                          "note": "achieved = SURVEY 8d algorithmic bytes (every candidate row counted at every visit) / "
-                                 "K1 stage time.  The implementation scores a hub's adjacency once per pass and builds "
-                                 "one root CDF per root (csrc/hub.cu), and re-read rows hit L2, so achieved exceeds the "
-                                 "HBM copy peak by design; executed_* counts the rows it really fetches (DESIGN.md 5)"},
+                                 "K1 stage time.  The implementation scores a hub's adjacency once per pass, builds one root "
+                                 "CDF per root and one step-1 CDF per (root, child) pair that several walks pick, and "
+                                 "re-read rows hit L2, so achieved exceeds the HBM copy peak by design; executed_* counts "
+                                 "the rows it really fetches (DESIGN.md 5); walk_kernel_ms is the whole gg_walk_sample call"},
             "walk": {"walks_per_step": W, "steps_per_neg_edge": c0["steps"] / max(c0["accepted"], 1),
                      "cands_per_neg_edge": c0["sum_l"] / max(c0["accepted"], 1), "ok_roots": c0["ok_roots"],
                      "bfs_build_s": t_bfs,

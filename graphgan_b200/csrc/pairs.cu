@@ -69,7 +69,7 @@ pair_grad_kernel(int mode, int B, int batch_total, const int *__restrict__ ni, c
 // ---------------------------------------------------------------- data-parallel merge (1 CTA)
 // Entry (r, s) = slot s of rank r's compact gradient.  Same unique + ordered segment-sum as above, on
 // ready-made row vectors; entry order is rank-major, so all ranks reduce in the same order.
-__global__ void __launch_bounds__(GRAD_THREADS, 1)
+__global__ void __launch_bounds__(MERGE_THREADS, 1)
 grad_merge_kernel(int world, int cap, int ld, const float *__restrict__ gathered, int *__restrict__ n_unique,
                   int *__restrict__ uniq_ids, float *__restrict__ grad_rows, float *__restrict__ grad_bias,
                   int *__restrict__ row_slot) {
@@ -81,7 +81,7 @@ grad_merge_kernel(int world, int cap, int ld, const float *__restrict__ gathered
     __shared__ int s_total;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t stride = (size_t)cap * ld + 2 * (size_t)cap + 4;   // == gg_grad_buf_floats
-    for (int t = tid; t < E; t += GRAD_THREADS) {
+    for (int t = tid; t < E; t += MERGE_THREADS) {
         const int r = t / cap, sidx = t % cap;
         const float *buf = gathered + (size_t)r * stride;
         const int nu = __float_as_int(buf[(size_t)cap * ld + 2 * (size_t)cap]);
@@ -91,7 +91,7 @@ grad_merge_kernel(int world, int cap, int ld, const float *__restrict__ gathered
     }
     __syncthreads();
     int base_total = 0;
-    for (int t0 = 0; t0 < E; t0 += GRAD_THREADS) {
+    for (int t0 = 0; t0 < E; t0 += MERGE_THREADS) {
         const int t = t0 + tid;
         int is_first = 0, first_t = t;
         if (t < E && ids[t] >= 0) {
@@ -126,11 +126,11 @@ grad_merge_kernel(int world, int cap, int ld, const float *__restrict__ gathered
     }
     if (tid == 0) { s_total = base_total; *n_unique = base_total; }
     __syncthreads();
-    for (int t = tid; t < E; t += GRAD_THREADS)
+    for (int t = tid; t < E; t += MERGE_THREADS)
         if (slot[t] < 0 && slot[t] != -(E + 1)) slot[t] = slot[-1 - slot[t]];
     __syncthreads();
     const int U = s_total;
-    for (int u = wid; u < U; u += GRAD_THREADS / 32) {
+    for (int u = wid; u < U; u += MERGE_THREADS / 32) {
         for (int c = 4 * lane; c < ld; c += 128) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int t = 0; t < E; ++t) {
@@ -243,7 +243,7 @@ extern "C" int gg_grad_merge(int32_t world, int32_t cap, int32_t ld, const float
     GG_REQUIRE(smem <= 200 * 1024, "merge exceeds shared memory");
     if (smem > 48 * 1024)
         GG_CHECK(cudaFuncSetAttribute(gg::grad_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gg::grad_merge_kernel<<<1, gg::GRAD_THREADS, smem, (cudaStream_t)stream>>>(world, cap, ld, gathered, n_unique, uniq_ids,
+    gg::grad_merge_kernel<<<1, gg::MERGE_THREADS, smem, (cudaStream_t)stream>>>(world, cap, ld, gathered, n_unique, uniq_ids,
                                                                              grad_rows, grad_bias, row_slot);
     return gg::check_cuda(cudaGetLastError(), "grad merge launch");
 }

@@ -4,6 +4,7 @@
 // the host-language overhead per step (argument marshalling, tensor slicing) would dominate.  This entry point
 // walks the caller's shuffled start list and enqueues every step on the stream; nothing synchronises.
 #include <math.h>
+#include <string.h>
 
 #include "update_dev.cuh"
 
@@ -56,6 +57,7 @@ struct LoopArgs {
     const int *node_id, *node_neighbor_id;
     const float *aux;
     float *emb, *m_emb, *v_emb, *bias, *m_bias, *v_bias;
+    float *emb2, *bias2;               // fused loop only: the second parameter buffers of the ping-pong
     float lambda;
     int *n_unique, *uniq_ids;
     float *grad_rows, *grad_bias;
@@ -119,6 +121,149 @@ __global__ void __launch_bounds__(NT, 1) train_loop_kernel(const __grid_constant
         a.sync_words[4] = (unsigned long long)c_wait; a.sync_words[5] = (unsigned long long)a.n_starts;
     }
 }
+
+// ---------------------------------------------------------------- fused step loop
+// One barrier per step instead of two.  EVERY CTA runs the forward pass and the unique/list construction of the
+// mini-batch redundantly (64 pairs: ~32 KB of rows from L2, identical results everywhere), then sweeps the rows it
+// owns; for an owned row with a gradient the sweeping lane accumulates its own columns of the segment sum from
+// the entry list (the same additions in the same order as pair_sums) and applies Adam at once.  Nothing is
+// published between CTAs except the parameters themselves, which ping-pong between two buffers: step s reads
+// (emb, bias) of parity s and writes parity s+1 -- the sweep writes every row, and a CTA that is already sweeping
+// cannot disturb a CTA that is still in its forward pass.  The barrier at the end of the step is the only
+// inter-CTA synchronisation.  m / v are updated in place (only their owner touches them).
+template <int NT, int UNR>
+__global__ void __launch_bounds__(NT, 1) train_fused_kernel(const __grid_constant__ LoopArgs a) {
+    extern __shared__ int smem[];
+    static_assert(UNR % 2 == 0, "both halves of a 256-wide row must be in flight in the same warp");
+    constexpr int W = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int *lslot = smem + 11 * a.batch_size + 8;   // [iters * RPC] owned row (local index) -> slot of this step, or -1
+    const int ld = a.ld, q = ld >> 2;
+    const int rps = q >= 32 ? 1 : 32 / q, halves = q > 32 ? q / 32 : 1;
+    const long long nseg = ((a.n_node + rps - 1) / rps) * halves;
+    const int sub = q >= 32 ? 0 : lane / q;
+    const int col = q >= 32 ? 4 * lane : 4 * (lane % q);
+    const int G = gridDim.x;
+    const int RPC = W * UNR * rps / halves;                    // rows of one (CTA, iteration) chunk
+    const long long seg_round = (long long)G * W * UNR;
+    const int iters = (int)((nseg + seg_round - 1) / seg_round);
+    const int tab_n = iters * RPC;
+    unsigned long long *done = a.sync_words + 1;
+    float b1p = a.beta1_power, b2p = a.beta2_power;
+    const float b1 = a.beta1, b2 = a.beta2, omb1 = 1.0f - b1, omb2 = 1.0f - b2, eps = a.eps, lambda = a.lambda;
+    const bool clk = blockIdx.x == 0 && tid == 0;
+    long long c_grad = 0, c_sweep = 0, c_wait = 0;
+    for (long long s = 0; s < a.n_starts; ++s) {
+        const long long t0 = clk ? clock64() : 0;
+        const float *E_old = (s & 1) ? a.emb2 : a.emb, *b_old = (s & 1) ? a.bias2 : a.bias;
+        float *E_new = (s & 1) ? a.emb : a.emb2, *b_new = (s & 1) ? a.bias : a.bias2;
+        const long long start = a.starts[s];
+        const int B = (int)((start + a.batch_size < a.n_rows ? start + a.batch_size : a.n_rows) - start);
+        for (int i = tid; i < tab_n; i += NT) lslot[i] = -1;
+        pair_lists<true, NT>(smem, a.mode, B, B, a.node_id + start, a.node_neighbor_id + start, a.aux + start, E_old, b_old, ld,
+                             nullptr, nullptr, nullptr);
+        const PairSmem ps = pair_smem(smem, B);
+        for (int t = tid; t < 2 * B; t += NT)
+            if (ps.rnk[t] == 0) {                              // first occurrence of its row
+                const int row = ps.ids[t];
+                const long long chunk = row / RPC;
+                if ((int)(chunk % G) == (int)blockIdx.x) lslot[(int)(chunk / G) * RPC + row % RPC] = ps.slot[t];
+            }
+        __syncthreads();
+        const long long t1 = clk ? clock64() : 0;
+        // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t): the same fp32 operation sequence as the host loop
+        const float lr_t = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+#define GG_ADAM1(f)                                                                                   \
+    m[k].f = __fadd_rn(__fmul_rn(m[k].f, b1), __fmul_rn(omb1, g.f));                                  \
+    v[k].f = __fadd_rn(__fmul_rn(v[k].f, b2), __fmul_rn(__fmul_rn(omb2, g.f), g.f));                  \
+    x[k].f = __fsub_rn(x[k].f, __fdiv_rn(__fmul_rn(lr_t, m[k].f), __fadd_rn(__fsqrt_rn(v[k].f), eps)));
+#define GG_ACC(f) g.f = __fadd_rn(g.f, __fadd_rn(__fmul_rn(dd[e], o[e].f), __fmul_rn(lambda, x[k].f)))
+        for (int it = 0; it < iters; ++it) {
+            const long long s0 = ((long long)it * G + blockIdx.x) * (W * UNR) + (long long)wid * UNR;
+            int row[UNR], cc[UNR], slot[UNR];
+            float4 m[UNR], v[UNR], x[UNR];
+            float xb[UNR], mb[UNR], vb[UNR];
+            // every load that does not depend on another load is issued here: parameters, Adam slots, the bias triple
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+                const long long seg = s0 + k;
+                const long long r = (seg / halves) * rps + sub;
+                cc[k] = col + 128 * (int)(seg % halves);
+                row[k] = (seg < nseg && r < a.n_node) ? (int)r : -1;
+                slot[k] = -1;
+                xb[k] = mb[k] = vb[k] = 0.0f;
+                if (row[k] >= 0) {
+                    const size_t at = (size_t)r * ld + cc[k];
+                    slot[k] = lslot[it * RPC + (int)(r % RPC)];
+                    m[k] = *reinterpret_cast<const float4 *>(a.m_emb + at);
+                    v[k] = *reinterpret_cast<const float4 *>(a.v_emb + at);
+                    x[k] = __ldcg(reinterpret_cast<const float4 *>(E_old + at));
+                    if (cc[k] == 0) { xb[k] = __ldcg(b_old + r); mb[k] = a.m_bias[r]; vb[k] = a.v_bias[r]; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UNR; ++k) {
+                if (row[k] < 0) continue;
+                const size_t at = (size_t)row[k] * ld + cc[k];
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                int lo = 0, n = 0;
+                if (slot[k] >= 0) { lo = ps.off[slot[k]]; n = ps.off[slot[k] + 1] - lo; }
+                for (int r2 = 0; r2 < n; r2 += 4) {            // pair_sums' additions for this lane's columns
+                    float4 o[4];
+                    float dd[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool in = r2 + e < n;
+                        const int t = in ? ps.lst[lo + r2 + e] : 0;
+                        o[e] = in ? __ldcg(reinterpret_cast<const float4 *>(E_old + (size_t)ps.ids[t < B ? t + B : t - B] * ld + cc[k]))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                        dd[e] = ps.delta[t < B ? t : t - B];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (r2 + e >= n) break;
+                        GG_ACC(x); GG_ACC(y); GG_ACC(z); GG_ACC(w);
+                    }
+                }
+                float gb = 0.0f;
+                if (cc[k] == 0) {                               // this lane also owns the row's bias
+                    for (int r2 = 0; r2 < n; ++r2) {            // j-side entries only; generator.py:28-29 has no bias l2
+                        const int t = ps.lst[lo + r2];
+                        if (t < B) continue;
+                        const float d = ps.delta[t - B];
+                        gb = __fadd_rn(gb, a.mode == 0 ? __fadd_rn(d, __fmul_rn(lambda, xb[k])) : d);
+                    }
+                }
+                GG_ADAM1(x) GG_ADAM1(y) GG_ADAM1(z) GG_ADAM1(w)
+                *reinterpret_cast<float4 *>(a.m_emb + at) = m[k];
+                *reinterpret_cast<float4 *>(a.v_emb + at) = v[k];
+                *reinterpret_cast<float4 *>(E_new + at) = x[k];
+                if (cc[k] == 0) {
+                    const float mm = __fadd_rn(__fmul_rn(mb[k], b1), __fmul_rn(omb1, gb));
+                    const float vv = __fadd_rn(__fmul_rn(vb[k], b2), __fmul_rn(__fmul_rn(omb2, gb), gb));
+                    a.m_bias[row[k]] = mm; a.v_bias[row[k]] = vv;
+                    b_new[row[k]] = __fsub_rn(xb[k], __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(__fsqrt_rn(vv), eps)));
+                }
+            }
+        }
+#undef GG_ACC
+#undef GG_ADAM1
+        b1p = __fmul_rn(b1p, b1);
+        b2p = __fmul_rn(b2p, b2);
+        __syncthreads();
+        const long long t2 = clk ? clock64() : 0;
+        if (tid == 0) {
+            add_release(done, 1ull);
+            while (ld_acquire(done) < (unsigned long long)G * (unsigned long long)(s + 1)) {}
+        }
+        __syncthreads();
+        if (clk) { c_grad += t1 - t0; c_sweep += t2 - t1; c_wait += clock64() - t2; }
+    }
+    if (clk) {
+        a.sync_words[2] = (unsigned long long)c_grad; a.sync_words[3] = (unsigned long long)c_sweep;
+        a.sync_words[4] = (unsigned long long)c_wait; a.sync_words[5] = (unsigned long long)a.n_starts;
+    }
+}
 }  // namespace
 }  // namespace gg
 
@@ -160,6 +305,60 @@ extern "C" int gg_train_loop(int32_t mode, int64_t n_rows, const int64_t *start_
                                          smem, (cudaStream_t)stream));
     // the accumulators advance deterministically: replay the fp32 products on the host
     for (int64_t s = 0; s < n_starts; ++s) {
+        volatile float p1 = *beta1_power * beta1, p2 = *beta2_power * beta2;
+        *beta1_power = p1;
+        *beta2_power = p2;
+    }
+    return 0;
+}
+
+extern "C" int gg_train_fused(int32_t mode, int64_t n_rows, const int64_t *start_list_dev, int64_t n_starts, int32_t batch_size,
+                              const int32_t *node_id, const int32_t *node_neighbor_id, const float *aux, int64_t n_node,
+                              int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias, float *v_bias,
+                              float *emb2, float *bias2, float lambda, float lr, float beta1, float beta2, float eps,
+                              float *beta1_power, float *beta2_power, uint64_t *sync_words, void *stream) {
+    GG_REQUIRE(start_list_dev && beta1_power && beta2_power && sync_words && emb2 && bias2, "null pointer");
+    GG_REQUIRE(emb && m_emb && v_emb && bias && m_bias && v_bias && node_id && node_neighbor_id && aux, "null pointer");
+    GG_REQUIRE(batch_size > 0 && batch_size <= GG_MAX_BATCH, "batch size out of range");
+    GG_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (discriminator) or 1 (generator)");
+    GG_REQUIRE(ld == 32 || ld == 64 || ld == 128 || ld == 256, "ld must be 32, 64, 128 or 256");
+    if (n_starts == 0) return 0;
+    constexpr int NT = 512, UNR = 2, W = NT / 32;
+    int dev = 0, coop = 0, per_sm = 0;
+    GG_CHECK(cudaGetDevice(&dev));
+    GG_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GG_REQUIRE(coop, "device does not support cooperative launches");
+    const int q = ld / 4, rps = q >= 32 ? 1 : 32 / q, halves = q > 32 ? q / 32 : 1;
+    const long long nseg = ((n_node + rps - 1) / rps) * halves;
+    long long ctas = (nseg + W * UNR - 1) / (W * UNR);          // one sweep iteration per warp when the graph is small
+    if (ctas > gg::sm_count()) ctas = gg::sm_count();
+    if (ctas < 1) ctas = 1;
+    const long long seg_round = ctas * W * UNR;
+    const long long iters = (nseg + seg_round - 1) / seg_round;
+    const long long tab_n = iters * (W * UNR * rps / halves);
+    const size_t smem = gg::pair_grad_smem_bytes(batch_size) + (size_t)tab_n * 4;
+    GG_REQUIRE(smem <= 200 * 1024, "graph too large for the fused step loop (use gg_train_steps)");
+    const void *kern = (const void *)gg::train_fused_kernel<NT, UNR>;
+    if (smem > 48 * 1024) GG_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GG_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gg::train_fused_kernel<NT, UNR>, NT, smem));
+    GG_REQUIRE(per_sm >= 1, "fused step loop kernel does not fit on an SM");
+    gg::LoopArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = mode; a.batch_size = batch_size; a.ld = ld; a.n_rows = n_rows; a.n_starts = n_starts; a.n_node = n_node;
+    a.starts = (const long long *)start_list_dev; a.node_id = node_id; a.node_neighbor_id = node_neighbor_id; a.aux = aux;
+    a.emb = emb; a.m_emb = m_emb; a.v_emb = v_emb; a.bias = bias; a.m_bias = m_bias; a.v_bias = v_bias;
+    a.emb2 = emb2; a.bias2 = bias2; a.lambda = lambda;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.beta1_power = *beta1_power; a.beta2_power = *beta2_power;
+    a.sync_words = (unsigned long long *)sync_words;
+    cudaStream_t st = (cudaStream_t)stream;
+    GG_CHECK(cudaMemsetAsync(sync_words, 0, 8 * sizeof(uint64_t), st));
+    void *args[] = {&a};
+    GG_CHECK(cudaLaunchCooperativeKernel(kern, dim3((unsigned)ctas), dim3(NT), args, smem, st));
+    if (n_starts & 1) {   // an odd number of steps leaves the parameters in the second buffers
+        GG_CHECK(cudaMemcpyAsync(emb, emb2, sizeof(float) * (size_t)n_node * ld, cudaMemcpyDeviceToDevice, st));
+        GG_CHECK(cudaMemcpyAsync(bias, bias2, sizeof(float) * (size_t)n_node, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int64_t s = 0; s < n_starts; ++s) {   // the accumulators advance deterministically: replay them on the host
         volatile float p1 = *beta1_power * beta1, p2 = *beta2_power * beta2;
         *beta1_power = p1;
         *beta2_power = p2;

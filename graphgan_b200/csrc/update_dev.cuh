@@ -7,7 +7,8 @@
 namespace gg {
 
 // ---------------------------------------------------------------- mini-batch gradient (1 CTA)
-constexpr int GRAD_THREADS = 1024;
+constexpr int GRAD_THREADS = 512;     // 128 registers per thread: the fused bodies do not spill (they do at 1024 / 64)
+constexpr int MERGE_THREADS = 1024;   // grad_merge_kernel (pairs.cu)
 
 // COH = true: the parameters may have been written earlier in the SAME kernel by other SMs (persistent step
 // loop): read them through L2 (ld.global.cg) instead of the non-coherent read-only path.
@@ -29,25 +30,33 @@ __device__ __forceinline__ float group_dot_t(const float *a, const float *b, int
 // Shared memory of one mini-batch gradient: ids, slot, rank, list (2B ints each), offsets (2B + 2), delta (B).
 __host__ __device__ inline size_t pair_grad_smem_bytes(int B) { return (size_t)(11 * B + 8) * 4; }
 
-// One mini-batch gradient, executed by one CTA of NT threads (a multiple of 32, at most 1024); smem: pair_grad_smem_bytes(B).
-//   forward     4 pairs per warp (8 lanes per dot, the canonical group dot), sigmoid in fp64
-//   unique      8 lanes per entry count the earlier equal ids (-> first occurrence and rank within the row's
-//               entries); a block scan numbers the first occurrences in entry order (TF's unique() order)
-//   lists       per-slot entry lists in entry order (CSR in shared memory: offsets by a second block scan)
-//   sums        8 lanes per slot walk the slot's list; two entries' rows are in flight per iteration and are
-//               added in entry order, so the sum is the same op sequence as a sequential IndexedSlices sum
-template <bool COH, int NT = GRAD_THREADS>
-__device__ __forceinline__ void pair_grad_body(int *smem, int mode, int B, int batch_total, const int *__restrict__ ni,
-                                               const int *__restrict__ nj, const float *__restrict__ aux,
-                                               const float *emb, const float *bias, int ld, float lambda, int *n_unique,
-                                               int *uniq_ids, float *grad_rows, float *grad_bias, int *row_slot) {
+// The shared-memory arrays of one mini-batch (carved from pair_grad_smem_bytes(B) bytes).
+struct PairSmem {
+    int *ids;      // [E]  entry -> row id (i-side entries first, then j-side);  E = 2B
+    int *slot;     // [E]  entry -> unique slot
+    int *rnk;      // [E]  entry -> number of earlier entries with the same id
+    int *lst;      // [E]  entries grouped by slot, entry order inside a slot
+    int *off;      // [E + 2] slot -> start of its list
+    float *delta;  // [B]  dL/dscore_k
+};
+__device__ __forceinline__ PairSmem pair_smem(int *smem, int B) {
     const int E = 2 * B;
-    int *ids = smem;              // [E]  entry -> row id (i-side entries first, then j-side)
-    int *slot = ids + E;          // [E]  entry -> unique slot
-    int *rnk = slot + E;          // [E]  entry -> number of earlier entries with the same id
-    int *lst = rnk + E;           // [E]  entries grouped by slot, entry order inside a slot
-    int *off = lst + E;           // [E + 2] slot -> start of its list
-    float *delta = reinterpret_cast<float *>(off + E + 2);  // [B] dL/dscore_k
+    PairSmem p;
+    p.ids = smem; p.slot = p.ids + E; p.rnk = p.slot + E; p.lst = p.rnk + E; p.off = p.lst + E;
+    p.delta = reinterpret_cast<float *>(p.off + E + 2);
+    return p;
+}
+
+// forward + unique + lists (see pair_grad_body).  Returns the number of unique rows U; uniq_ids / row_slot /
+// n_unique (global) are written only when uniq_ids is not null.
+template <bool COH, int NT>
+__device__ __forceinline__ int pair_lists(int *smem, int mode, int B, int batch_total, const int *__restrict__ ni,
+                                          const int *__restrict__ nj, const float *__restrict__ aux, const float *emb,
+                                          const float *bias, int ld, int *n_unique, int *uniq_ids, int *row_slot) {
+    const int E = 2 * B;
+    const PairSmem ps = pair_smem(smem, B);
+    int *ids = ps.ids, *slot = ps.slot, *rnk = ps.rnk, *lst = ps.lst, *off = ps.off;
+    float *delta = ps.delta;
     __shared__ int s_warp[32];
     __shared__ int s_total;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, grp = lane >> 3, g = lane & 7;
@@ -118,11 +127,11 @@ __device__ __forceinline__ void pair_grad_body(int *smem, int mode, int B, int b
         __syncthreads();
         const int excl = base_total + (wid ? s_warp[wid - 1] : 0) + x - is_first;
         if (t < E) slot[t] = is_first ? excl : -1 - first_t;  // non-first: remember where the first is
-        if (t < E && is_first) { uniq_ids[excl] = ids[t]; row_slot[ids[t]] = excl; }
+        if (t < E && is_first && uniq_ids) { uniq_ids[excl] = ids[t]; row_slot[ids[t]] = excl; }
         base_total += s_warp[31];
         __syncthreads();
     }
-    if (tid == 0) { s_total = base_total; *n_unique = base_total; }
+    if (tid == 0) { s_total = base_total; if (uniq_ids) *n_unique = base_total; }
     // non-first entries take the slot of their first occurrence (which is >= 0 and final); count the list lengths
     for (int t = tid; t < E; t += NT) {
         int sl = slot[t];
@@ -162,6 +171,17 @@ __device__ __forceinline__ void pair_grad_body(int *smem, int mode, int B, int b
     }
     for (int t = tid; t < E; t += NT) lst[off[slot[t]] + rnk[t]] = t;
     __syncthreads();
+    return U;
+}
+
+// segment sums of the lists built by pair_lists -> grad_rows [U, ld], grad_bias [U]
+template <bool COH, int NT>
+__device__ __forceinline__ void pair_sums(int *smem, int mode, int B, int U, const float *emb, const float *bias, int ld,
+                                          float lambda, float *grad_rows, float *grad_bias) {
+    const PairSmem ps = pair_smem(smem, B);
+    const int *ids = ps.ids, *lst = ps.lst, *off = ps.off;
+    const float *delta = ps.delta;
+    const int tid = threadIdx.x, g = tid & 7;
     // ---- segment sums: 8 lanes per slot, columns in passes of 64 (one float4 at c and one at c + 32 per lane)
     for (int u0 = 0; u0 < U; u0 += NT / 8) {
         const int u = u0 + (tid >> 3);
@@ -180,24 +200,26 @@ __device__ __forceinline__ void pair_grad_body(int *smem, int mode, int B, int b
             // sum of the numpy oracle, so cancellation noise in near-zero coordinates stays comparable.
 #define GG_ACC(acc, o, self, f) acc.f = __fadd_rn(acc.f, __fadd_rn(__fmul_rn(d, o.f), __fmul_rn(lambda, self.f)))
 #define GG_ACC4(acc, o, self) GG_ACC(acc, o, self, x); GG_ACC(acc, o, self, y); GG_ACC(acc, o, self, z); GG_ACC(acc, o, self, w)
-            int r = 0;
-            for (; r + 1 < n; r += 2) {
-                const int ta = lst[lo + r], tb = lst[lo + r + 1];
-                const float *oa = emb + (size_t)ids[ta < B ? ta + B : ta - B] * ld + c;
-                const float *ob = emb + (size_t)ids[tb < B ? tb + B : tb - B] * ld + c;
-                const float4 a0 = row4<COH>(oa), b0 = row4<COH>(ob);
-                const float4 a1 = two ? row4<COH>(oa + 32) : z, b1 = two ? row4<COH>(ob + 32) : z;
-                float d = delta[ta < B ? ta : ta - B];
-                GG_ACC4(acc0, a0, self0); GG_ACC4(acc1, a1, self1);
-                d = delta[tb < B ? tb : tb - B];
-                GG_ACC4(acc0, b0, self0); GG_ACC4(acc1, b1, self1);
-            }
-            if (r < n) {
-                const int ta = lst[lo + r];
-                const float *oa = emb + (size_t)ids[ta < B ? ta + B : ta - B] * ld + c;
-                const float4 a0 = row4<COH>(oa), a1 = two ? row4<COH>(oa + 32) : z;
-                const float d = delta[ta < B ? ta : ta - B];
-                GG_ACC4(acc0, a0, self0); GG_ACC4(acc1, a1, self1);
+            // four entries' rows in flight, added in entry order (a centre node repeated through a whole batch gives
+            // one slot a list of ~B entries: the loads must not be serialised behind the adds)
+            for (int r = 0; r < n; r += 4) {
+                float4 o0[4], o1[4];
+                float dd[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool in = r + e < n;
+                    const int t = in ? lst[lo + r + e] : 0;
+                    const float *op = emb + (size_t)ids[t < B ? t + B : t - B] * ld + c;
+                    o0[e] = in ? row4<COH>(op) : z;
+                    o1[e] = (in && two) ? row4<COH>(op + 32) : z;
+                    dd[e] = delta[t < B ? t : t - B];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (r + e >= n) break;
+                    const float d = dd[e];
+                    GG_ACC4(acc0, o0[e], self0); GG_ACC4(acc1, o1[e], self1);
+                }
             }
 #undef GG_ACC4
 #undef GG_ACC
@@ -216,6 +238,23 @@ __device__ __forceinline__ void pair_grad_body(int *smem, int mode, int B, int b
             grad_bias[u] = gb;
         }
     }
+}
+
+
+// One mini-batch gradient, executed by one CTA of NT threads (a multiple of 32, at most 1024); smem: pair_grad_smem_bytes(B).
+//   forward     4 pairs per warp (8 lanes per dot, the canonical group dot), sigmoid in fp64
+//   unique      8 lanes per entry count the earlier equal ids (-> first occurrence and rank within the row's
+//               entries); a block scan numbers the first occurrences in entry order (TF's unique() order)
+//   lists       per-slot entry lists in entry order (CSR in shared memory: offsets by a second block scan)
+//   sums        8 lanes per slot walk the slot's list; two entries' rows are in flight per iteration and are
+//               added in entry order, so the sum is the same op sequence as a sequential IndexedSlices sum
+template <bool COH, int NT = GRAD_THREADS>
+__device__ __forceinline__ void pair_grad_body(int *smem, int mode, int B, int batch_total, const int *__restrict__ ni,
+                                               const int *__restrict__ nj, const float *__restrict__ aux,
+                                               const float *emb, const float *bias, int ld, float lambda, int *n_unique,
+                                               int *uniq_ids, float *grad_rows, float *grad_bias, int *row_slot) {
+    const int U = pair_lists<COH, NT>(smem, mode, B, batch_total, ni, nj, aux, emb, bias, ld, n_unique, uniq_ids, row_slot);
+    pair_sums<COH, NT>(smem, mode, B, U, emb, bias, ld, lambda, grad_rows, grad_bias);
 }
 
 

@@ -536,10 +536,16 @@ __global__ void finalize_kernel(long long n_roots, const long long *walk_ptr, in
     const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= n_roots) return;
     const long long w0 = walk_ptr[slot], w1 = walk_ptr[slot + 1];
-    // first walk that is not DONE (void, skipped or never run)
+    // first walk that is not DONE (void, skipped or never run); four independent loads in flight per lane (a hub
+    // root has > 10 k walks and one warp)
     long long first_bad = w1;
-    for (long long w = w0 + lane; w < w1; w += 32)
-        if (status[w] != GG_DONE) { first_bad = w; break; }
+    for (long long w = w0 + lane; w < w1 && first_bad == w1; w += 128) {
+        int st[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st[q] = (w + 32 * q < w1) ? status[w + 32 * q] : GG_DONE;
+#pragma unroll
+        for (int q = 3; q >= 0; --q) if (st[q] != GG_DONE) first_bad = w + 32 * q;
+    }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
         const long long o = __shfl_xor_sync(FULL, first_bad, off);
@@ -547,17 +553,27 @@ __global__ void finalize_kernel(long long n_roots, const long long *walk_ptr, in
     }
     const bool ok = (first_bad == w1) && (w1 > w0);
     unsigned long long steps = 0, suml = 0;
-    for (long long w = w0 + lane; w < w1; w += 32) {
-        if (w <= first_bad) {
-            steps += (unsigned)wsteps[w]; suml += (unsigned)wsuml[w];
-            if (for_d && status[w] == GG_DONE) {
-                const int e = first_edge[w];
-                if (e >= 0) atomicOr(d1_bits + (e >> 5), 1u << (e & 31));
+    for (long long wb = w0 + lane; wb < w1; wb += 128) {
+        int st[4], ws[4], wl[4], fe[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long w = wb + 32 * q;
+            const bool in = w < w1 && w <= first_bad;
+            st[q] = in ? status[w] : GG_NOTRUN; ws[q] = in ? wsteps[w] : 0; wl[q] = in ? wsuml[w] : 0;
+            fe[q] = (in && for_d) ? first_edge[w] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long w = wb + 32 * q;
+            if (w >= w1) break;
+            if (w <= first_bad) {
+                steps += (unsigned)ws[q]; suml += (unsigned)wl[q];
+                if (for_d && st[q] == GG_DONE && fe[q] >= 0) atomicOr(d1_bits + (fe[q] >> 5), 1u << (fe[q] & 31));
+            } else {  // the reference never ran these (graph_gan.py:252-257 returned early)
+                if (status[w] != GG_SKIPPED) status[w] = GG_NOTRUN;
+                samples[w] = -1; wsteps[w] = 0; wsuml[w] = 0;
+                if (path_len) path_len[w] = 0;
             }
-        } else {  // the reference never ran these (graph_gan.py:252-257 returned early)
-            if (status[w] != GG_SKIPPED) status[w] = GG_NOTRUN;
-            samples[w] = -1; wsteps[w] = 0; wsuml[w] = 0;
-            if (path_len) path_len[w] = 0;
         }
     }
 #pragma unroll

@@ -55,6 +55,7 @@ class PairModel:
         self.n_unique = torch.zeros(1, dtype=torch.int32, device=dev)
         self.sync_words = torch.zeros(8, dtype=torch.int64, device=dev)     # flag, counter, cycle breakdown of gg_train_loop
         self.grad_rows = z(2 * MAX_BATCH, self.ld)
+        self._emb2 = self._bias2 = None          # second parameter buffers of gg_train_fused (allocated on first use)
         self.grad_bias = z(2 * MAX_BATCH)
         # tf.train.AdamOptimizer defaults
         self.lr, self.lam = np.float32(lr), np.float32(lam)
@@ -110,18 +111,30 @@ class PairModel:
             raise ValueError("batch of %d pairs exceeds GG_MAX_BATCH=%d" % (batch_size, MAX_BATCH))
         b1p, b2p = C.c_float(float(self.beta1_power)), C.c_float(float(self.beta2_power))
         if persistent is None:
-            # the persistent loop wins while the dense sweep (E, m, v) stays in L2 (13.5 vs 18.7 us/step at C1); a sweep
-            # that streams from HBM is faster as its own full-occupancy launch (0.83 vs 1.0 ms/step at N = 1M, ld = 128)
-            persistent = 12 * self.n_node * self.ld <= (32 << 20)
-        if persistent:   # one cooperative launch for the whole start list (csrc/steps.cu: train_loop_kernel)
+            # the persistent loops win while the sweep is small (C1, 4 MB of E/m/v: 11.0 us/step fused, 13.9 two-barrier, 18.4
+            # as two launches per step); from ~60 MB on the sweep is faster as its own full-occupancy launch (N = 40k,
+            # ld = 128: 42.9 us against 45.5; N = 1M: 0.83 ms against 1.0 ms)
+            persistent = 12 * self.n_node * self.ld <= (16 << 20)
+        if persistent:
             starts_d = self.torch.as_tensor(starts).to(self.device)
-            _cabi.check(self.lib.gg_train_loop(self._step_mode, int(i.shape[0]), ptr(starts_d), int(starts.size),
-                                               int(batch_size), ptr(i), ptr(j), ptr(a), self.n_node, self.ld, ptr(self.emb),
-                                               ptr(self.m_emb), ptr(self.v_emb), ptr(self.bias_t), ptr(self.m_bias), ptr(self.v_bias),
-                                               C.c_float(float(self.lam)), ptr(self.n_unique), ptr(self.uniq_ids), ptr(self.grad_rows),
-                                               ptr(self.grad_bias), ptr(self.row_slot), C.c_float(float(self.lr)),
-                                               C.c_float(float(self.beta1)), C.c_float(float(self.beta2)), C.c_float(float(self.eps)),
-                                               C.byref(b1p), C.byref(b2p), ptr(self.sync_words), self._stream()), "gg_train_loop")
+            if persistent == "two-barrier":   # gg_train_loop: CTA 0 computes the gradient, flag, sweep, counter
+                _cabi.check(self.lib.gg_train_loop(self._step_mode, int(i.shape[0]), ptr(starts_d), int(starts.size),
+                                                   int(batch_size), ptr(i), ptr(j), ptr(a), self.n_node, self.ld, ptr(self.emb),
+                                                   ptr(self.m_emb), ptr(self.v_emb), ptr(self.bias_t), ptr(self.m_bias), ptr(self.v_bias),
+                                                   C.c_float(float(self.lam)), ptr(self.n_unique), ptr(self.uniq_ids), ptr(self.grad_rows),
+                                                   ptr(self.grad_bias), ptr(self.row_slot), C.c_float(float(self.lr)),
+                                                   C.c_float(float(self.beta1)), C.c_float(float(self.beta2)), C.c_float(float(self.eps)),
+                                                   C.byref(b1p), C.byref(b2p), ptr(self.sync_words), self._stream()), "gg_train_loop")
+            else:                              # gg_train_fused: one barrier per step, parameters ping-pong
+                if self._emb2 is None:
+                    self._emb2, self._bias2 = self.torch.empty_like(self.emb), self.torch.empty_like(self.bias_t)
+                _cabi.check(self.lib.gg_train_fused(self._step_mode, int(i.shape[0]), ptr(starts_d), int(starts.size),
+                                                    int(batch_size), ptr(i), ptr(j), ptr(a), self.n_node, self.ld, ptr(self.emb),
+                                                    ptr(self.m_emb), ptr(self.v_emb), ptr(self.bias_t), ptr(self.m_bias), ptr(self.v_bias),
+                                                    ptr(self._emb2), ptr(self._bias2), C.c_float(float(self.lam)),
+                                                    C.c_float(float(self.lr)), C.c_float(float(self.beta1)), C.c_float(float(self.beta2)),
+                                                    C.c_float(float(self.eps)), C.byref(b1p), C.byref(b2p), ptr(self.sync_words),
+                                                    self._stream()), "gg_train_fused")
             self._keep = (starts_d, i, j, a)     # keep the device arrays alive until the stream has consumed them
             self.beta1_power, self.beta2_power = np.float32(b1p.value), np.float32(b2p.value)
             self.step_count += int(starts.size)

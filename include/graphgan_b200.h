@@ -230,6 +230,17 @@ int gg_train_loop(int32_t mode, int64_t n_rows, const int64_t *start_list_dev, i
                   float beta1, float beta2, float eps, float *beta1_power, float *beta2_power, uint64_t *sync_words,
                   void *stream);
 
+/* The same loop with ONE inter-CTA barrier per step (csrc/steps.cu: train_fused_kernel): every CTA rebuilds the
+ * mini-batch's forward pass and entry lists, sweeps the rows it owns and accumulates their gradient on the fly;
+ * parameters ping-pong between (emb, bias) and the caller's second buffers (emb2 [N, ld], bias2 [N]); the result is
+ * always left in (emb, bias).  For graphs whose (E, m, v) stay in L2; returns an error when the per-CTA row table
+ * does not fit in shared memory.  grad_rows / uniq_ids / row_slot are not used.  Bit-identical to gg_train_steps. */
+int gg_train_fused(int32_t mode, int64_t n_rows, const int64_t *start_list_dev, int64_t n_starts, int32_t batch_size,
+                   const int32_t *node_id, const int32_t *node_neighbor_id, const float *aux, int64_t n_node, int32_t ld,
+                   float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias, float *v_bias, float *emb2,
+                   float *bias2, float lambda, float lr, float beta1, float beta2, float eps, float *beta1_power,
+                   float *beta2_power, uint64_t *sync_words, void *stream);
+
 /* get_node_pairs_from_path (graph_gan.py:272-291) for a batch of recorded paths.
  * pair_ptr: device [W+1] (out, exclusive scan of per-path pair counts). */
 int gg_window_pairs(int64_t n_walks, const int32_t *paths, const int32_t *path_len, int32_t max_path,

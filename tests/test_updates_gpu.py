@@ -227,27 +227,36 @@ def test_trainer_epoch_on_cagrqc(cuda_device, tmp_path, monkeypatch):
     assert s is None or (len(s) == 3 and all(q[-1] == q[-3] for q in p))
 
 
-def test_train_steps_equals_step_by_step(cuda_device):
-    """gg_train_steps (the C-driven batch loop) == calling d_step / g_step per batch, bit for bit, including the
-    short last batch and the beta-power bookkeeping."""
+@pytest.mark.parametrize("n,d,M,repeat", [(700, 50, 1000, 1), (300, 200, 1100, 24), (5000, 128, 1100, 3)])
+def test_train_steps_equals_step_by_step(n, d, M, repeat, cuda_device):
+    """The three batch loops -- gg_train_steps (two launches per step from C), gg_train_loop (persistent, two
+    barriers per step) and gg_train_fused (persistent, one barrier, ping-pong parameters) -- equal calling
+    d_step / g_step per batch, bit for bit: short last batch, odd and even step counts, centre nodes repeated through
+    a batch (long entry lists), ld = 64 / 128 / 256, and the beta-power bookkeeping."""
     import torch
     from graphgan_b200.discriminator import Discriminator
     from graphgan_b200.generator import Generator
     rs = np.random.RandomState(21)
-    n, d, M, B = 700, 50, 1000, 64
+    B = 64
     emb = rs.normal(0, 0.5, size=(n, d))
-    i, j = rs.randint(0, n, M).astype(np.int32), rs.randint(0, n, M).astype(np.int32)
+    i = np.repeat(rs.randint(0, n, M // repeat + 1), repeat)[:M].astype(np.int32)
+    j = rs.randint(0, n, M).astype(np.int32)
     starts = list(range(0, M, B))
     rs.shuffle(starts)
     for cls, aux in ((Discriminator, (rs.random_sample(M) < 0.5).astype(np.float32)), (Generator, (rs.random_sample(M) * 3).astype(np.float32))):
-        a, b = cls(n, emb, device=cuda_device), cls(n, emb, device=cuda_device)
+        a = cls(n, emb, device=cuda_device)
         for s0 in starts:
             a.step(i[s0:s0 + B], j[s0:s0 + B], aux[s0:s0 + B])
-        b.train_steps(i, j, aux, starts, B, persistent=False)
-        c = cls(n, emb, device=cuda_device)
-        c.train_steps(i, j, aux, starts, B, persistent=True)      # one cooperative launch (train_loop_kernel)
-        assert torch.equal(a.emb, c.emb) and torch.equal(a.bias_t, c.bias_t) and torch.equal(a.m_emb, c.m_emb)
-        assert a.beta1_power == c.beta1_power and a.step_count == c.step_count and int((c.row_slot != -1).sum()) == 0
-        assert torch.equal(a.emb, b.emb) and torch.equal(a.bias_t, b.bias_t) and torch.equal(a.v_emb, b.v_emb)
-        assert a.beta1_power == b.beta1_power and a.beta2_power == b.beta2_power and a.step_count == b.step_count
-        assert float(a.lr_t()) == float(b.lr_t())
+        for how, n_steps in ((False, len(starts)), ("two-barrier", len(starts)), (True, len(starts)), (True, len(starts) - 1), (None, 3)):
+            b = cls(n, emb, device=cuda_device)
+            b.train_steps(i, j, aux, starts[:n_steps], B, persistent=how)
+            if n_steps != len(starts):     # the reference run for a different number of steps
+                a2 = cls(n, emb, device=cuda_device)
+                for s0 in starts[:n_steps]:
+                    a2.step(i[s0:s0 + B], j[s0:s0 + B], aux[s0:s0 + B])
+            else:
+                a2 = a
+            for name in ("emb", "bias_t", "m_emb", "v_emb", "m_bias", "v_bias"):
+                assert torch.equal(getattr(a2, name), getattr(b, name)), (how, n_steps, name)
+            assert a2.beta1_power == b.beta1_power and a2.beta2_power == b.beta2_power and a2.step_count == b.step_count
+            assert float(a2.lr_t()) == float(b.lr_t()) and int((b.row_slot != -1).sum()) == 0
