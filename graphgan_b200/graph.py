@@ -58,6 +58,17 @@ class HostGraph:
         self.max_deg = int(np.diff(self.indptr).max()) if n else 0
 
     @classmethod
+    def from_arrays(cls, n_node, raw_indptr, raw_adj, indptr, adj):
+        """Re-create a HostGraph from the four arrays a previous instance held (e.g. a cache on disk)."""
+        g = cls.__new__(cls)
+        g.n_node = int(n_node)
+        g.raw_indptr, g.raw_adj = np.asarray(raw_indptr, np.int64), np.asarray(raw_adj, np.int32)
+        g.indptr, g.adj = np.asarray(indptr, np.int64), np.asarray(adj, np.int32)
+        assert g.raw_indptr.shape == g.indptr.shape == (g.n_node + 1,)
+        g.max_deg = int(np.diff(g.indptr).max()) if g.n_node else 0
+        return g
+
+    @classmethod
     def from_files(cls, train_filename, test_filename=""):
         """utils.read_edges(train_filename, test_filename) (src/utils.py:12-47)."""
         return cls(read_edge_file(train_filename), read_edge_file(test_filename))

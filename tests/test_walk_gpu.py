@@ -58,6 +58,26 @@ def test_bfs_matches_reference_order(name, cuda_device):
         assert np.array_equal(got, case["parent"][roots])
 
 
+def test_bfs_beyond_the_shared_memory_bitmap(cuda_device):
+    """N = 1.8 M nodes: the visited bitmap (N bits) no longer fits in shared memory and lives in the per-CTA global
+    scratch (csrc/bfs.cu: bitmap_in_smem = 0).  Same parents as the sequential FIFO BFS, deep sparse trees included
+    (avg degree 3: hundreds of levels of small frontiers)."""
+    import torch
+    from graphgan_b200 import graph as G, sampler as S, synth
+    from oracle import canonical as can
+    n = 1_800_000
+    edges = synth.power_law(n, 3, seed=9)
+    hg = G.HostGraph(edges, None, n_node=n)
+    dg = G.DeviceGraph(hg, cuda_device)
+    smp = S.WalkSampler(dg)
+    roots = synth.pick_roots(hg.degrees(), 6, seed=4)
+    trees = smp.build_trees(roots)
+    got = trees.parent.cpu().numpy()
+    want = can.bfs_parents(hg.indptr, hg.adj, roots)
+    assert np.array_equal(got, want)
+    assert (got >= 0).sum() > 6 * 1000            # the roots' components are not trivial
+
+
 @pytest.mark.parametrize("hub", [0, 8])
 @pytest.mark.parametrize("name", ["tiny", "rand300", "rand1200", "cagrqc"])
 def test_stream_replay_matches_reference(name, hub, cuda_device):
