@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_updates_gpu.py -q -m gpu -x 2>&1 | tail -3
-timeout 300 python tools/bench_updates.py 2>&1 | tail -12
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:train_fused -c 1 -o gpurun_out/prof_fused python tools/prof_updates.py fused 1000 > gpurun_out/ncu_fused.log 2>&1; tail -2 gpurun_out/ncu_fused.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|pair_grad_kernel" -s 20 -c 2 -o gpurun_out/prof_steps python tools/prof_updates.py steps 50 > gpurun_out/ncu_steps.log 2>&1; tail -2 gpurun_out/ncu_steps.log
+nproc; free -g | head -2; df -h /dev/shm | tail -1
+( time timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ) 2> gpurun_out/bench_ref.time; cat gpurun_out/bench_ref.time; cut -c1-200 gpurun_out/bench_ref.json; tail -c 500 gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
+timeout 900 python -m pytest tests/test_walk_gpu.py -q -m gpu -x -k "bfs" 2>&1 | tail -3
+( time python bench.py --no-cpu-baseline > gpurun_out/b_cached.json 2> gpurun_out/b_cached.err ) 2>&1 | grep real; python -c "
+import json; d=json.load(open('gpurun_out/b_cached.json')); print(d['value']/1e6, d['ms_per_step'], d['roofline']['traffic'], d['roofline']['frac'])"
