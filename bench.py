@@ -167,6 +167,18 @@ def _bfs_chunk(rng):
     return hi - lo
 
 
+def _one_thread():
+    """Pool initializer: one BLAS/OpenMP thread per worker process (the pool already uses every core; without this each
+    of the C workers starts C BLAS threads and the box thrashes -- measured 50x slower per core on 128 cores)."""
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        import threadpoolctl
+        _SH["_limit"] = threadpoolctl.threadpool_limits(limits=1)
+    except Exception:      # noqa: BLE001 -- best effort
+        pass
+
+
 def _sample_roots(job):
     """The reference's prepare_data_for_d -> sample(for_d=True) (oracle T0, lazy score) over sample[idx]."""
     from oracle import faithful
@@ -231,7 +243,7 @@ class CpuReference:
         _SH["par"] = par
         self.chunks = [(int(c[0]), int(c[-1]) + 1) for c in np.array_split(np.arange(n), min(workers, n)) if len(c)]
         if len(self.chunks) > 1:
-            self.pool = self.mp.Pool(len(self.chunks))     # forked AFTER _SH is complete: the workers inherit it
+            self.pool = self.mp.Pool(len(self.chunks), initializer=_one_thread)   # forked AFTER _SH is complete
         if parent_rows is not None:
             par[:] = parent_rows(self.sample)
         elif self.pool is None:
