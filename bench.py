@@ -307,7 +307,7 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, hg, d), "cpu_baseline": last,
             "e2e": {"value": v, "unit": "neg_edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -486,14 +486,34 @@ def run_b200(args):
             ref = CpuReference(hg, emb_h, roots, args.cpu_seconds, 1, parent_rows=parent_rows)
             line["cpu_baseline"] = ref.run(args.seed)[0]
             ref.close()
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; anything libraries print meanwhile (NCCL's version banner on some
+    boxes, torchrun notices) was routed to stderr by main()."""
+    sys.stdout.flush()
+    if _RESULT_FD is not None:
+        os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line))
+        sys.stdout.flush()
+
+
 def main():
+    global _RESULT_FD
     args = parse()
+    try:       # keep fd 1 for the result line only
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+    except OSError:
+        _RESULT_FD = None
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
