@@ -199,8 +199,9 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
 
 // ---------------------------------------------------------------- depth-1 reuse (Philox mode)
 // root_step_kernel: the root step of every walk (one thread per walk inverts the root's CDF) and a count of
-// the walks per (root, depth-1 child).  step1_cdf_kernel: for every pair that was picked at least once, the
-// child's candidate list / softmax / normalised CDF, built ONCE (walk_kernel then inverts it per walk).
+// the walks per (root, depth-1 child).  step1_cdf_kernel: for every pair picked by >= S1_MIN_WALKS walks, the
+// child's candidate list / softmax / un-normalised CDF + total, built ONCE (walk_kernel then inverts it per walk;
+// a pair picked once is cheaper inside its walk, which needs no CDF array).
 __global__ void root_step_kernel(const __grid_constant__ gg_walk_desc d) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= d.n_walks) return;

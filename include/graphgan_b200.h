@@ -111,14 +111,16 @@ typedef struct gg_walk_desc {
     const int32_t *walk_slot;   /* optional device [W]: root slot of every walk (saves a binary search per walk) */
     /* optional depth-1 reuse (GG_RNG_PHILOX, needs root_q + walk_slot): the walks of a root that pick the same
        depth-1 child share one candidate list.  gg_walk_sample first runs the root step of every walk and counts
-       the walks per (root, child) pair, builds the normalised CDF of every pair that occurs, and the walk kernel
-       then only inverts it.  Indexing: pair (root slot k, i-th neighbour) <-> pos = rq_ptr[k] + i, pos < s1_nq. */
+       the walks per (root, child) pair, builds the candidate ids and the un-normalised canonical CDF (plus its
+       total) of every pair picked by at least two walks, and the walk kernel then only inverts it (pairs picked
+       once are handled inside their walk).  Indexing: pair (root slot k, i-th neighbour) <-> pos = rq_ptr[k] + i,
+       pos < s1_nq. */
     int64_t s1_nq;              /* = rq_ptr[R] */
     const int32_t *s1_slot;     /* device [s1_nq] root slot of every pair */
     const int64_t *s1_ptr;      /* device [s1_nq+1] exclusive prefix of (degree(child) + 1): pool offsets */
     int32_t *s1_cnt;            /* device [s1_nq] scratch: walks per pair */
     int32_t *s1_n;              /* device [s1_nq] out: list length of a pair (0 = void) */
-    double *s1_q;               /* device pool [s1_ptr[s1_nq]]: normalised CDFs */
+    double *s1_q;               /* device pool [s1_ptr[s1_nq]]: per pair c[0..n-1] = carry + scan(e/S), c[n] = total */
     int32_t *s1_ids;            /* device pool: candidate ids */
     int32_t *first_idx;         /* device [W] scratch: root-step choice of every walk */
     const int32_t *s1_order;    /* optional device [s1_nq]: the (root, child) pairs sorted by decreasing child degree; with it

