@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-( time timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ) 2> gpurun_out/bench_ref.time; grep real gpurun_out/bench_ref.time; cut -c1-160 gpurun_out/bench_ref.json; tail -c 700 gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
-( time timeout 1200 python bench.py --workload powerlaw_10m --no-cpu-baseline --steps 10 --warmup 3 > gpurun_out/bench_10m.json 2> gpurun_out/bench_10m.err ) 2>&1 | grep real; cat gpurun_out/bench_10m.json | cut -c1-1500; tail -5 gpurun_out/bench_10m.err
+timeout 300 python -m pytest tests/test_updates_gpu.py -q -m gpu -x 2>&1 | tail -2
+timeout 200 python tools/bench_updates.py 1000000 128 64 300 2>&1 | grep -v "CTA 0" | tail -6
+timeout 200 python tools/bench_updates.py 2>&1 | grep -v "CTA 0" | tail -6

@@ -1,4 +1,4 @@
-"""Tiny driver for ncu captures of the step-loop kernels: python tools/prof_updates.py {fused|loop|steps} [n_steps]"""
+"""Tiny driver for ncu captures of the step-loop kernels: python tools/prof_updates.py {fused|loop|steps} [n_steps [n_node n_emb]]"""
 import sys
 
 import numpy as np
@@ -9,7 +9,7 @@ from graphgan_b200.generator import Generator        # noqa: E402
 
 how = {"fused": True, "loop": "two-barrier", "steps": False}[sys.argv[1]]
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
-n, n_emb, B = 5242, 50, 64
+n, n_emb, B = (int(sys.argv[3]), int(sys.argv[4]), 64) if len(sys.argv) > 4 else (5242, 50, 64)
 rng = np.random.default_rng(0)
 init = (rng.standard_normal((n, n_emb)) * 0.1).astype(np.float32)
 P = B * 4096
