@@ -157,7 +157,7 @@ class WalkSampler:
         self.chunk_walks = int(chunk_walks)
         # one CDF per (root, depth-1 child) pair that occurs (needs reuse): the walks of a root that pick the same child
         # share its candidate list (5.5x fewer neighbour probes at step 1 on C3); the builder kernel pulls the pairs
-        # from a queue, largest lists first (hub_first), because a 13.8k-entry hub list occupies one warp for ~1 ms
+        # from a queue, largest lists first (hub_first), because a 13.8k-entry hub list occupies one warp for ~0.5-1 ms
         self.depth1 = bool(depth1)
         self.hub_first = bool(hub_first)          # start order of the walks (WalkPlan.start_order); results do not depend on it
         nbytes = C.c_int64(0)
