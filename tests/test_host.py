@@ -180,3 +180,23 @@ def test_bench_reference_arm_machinery():
     for workers, (res, n_sample, deg_sum) in out.items():
         edges = int(re.search(r"\((\d+) neg edges", res["sample"]).group(1))
         assert 0 < edges <= deg_sum and n_sample >= 2
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): exactly one line on stdout, valid JSON with
+    the contract's keys; runs on the host cores only (no GPU, nothing read from /root/reference)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "powerlaw_100k",
+                          "--steps", "1", "--warmup", "0", "--roots", "256"], capture_output=True, text=True, timeout=600,
+                         cwd=ROOT, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "neg_edges/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "neg_edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "R=256" in d["config"]["workload"]
