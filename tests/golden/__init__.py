@@ -1,0 +1,1 @@
+"""Golden fixtures generated from the unmodified reference (make_golden.py) and their loader."""
