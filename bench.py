@@ -294,7 +294,7 @@ def run_reference(args):
         return 0
     hg, emb, roots, d = make_inputs(args, 0)
     workers = os.cpu_count() or 1
-    per_step_seconds = max(2.0, min(args.cpu_seconds, 150.0 / max(args.steps + args.warmup, 1)))
+    per_step_seconds = max(0.5, min(args.cpu_seconds, 150.0 / max(args.steps + args.warmup, 1)))   # whole run: a few minutes
     ref = CpuReference(hg, emb, roots, per_step_seconds, workers)
     times, vals, last = [], [], None
     for s in range(args.warmup + args.steps):
