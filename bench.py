@@ -49,8 +49,6 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--hub-threshold", type=int, default=128, help="degree from which adjacency scores are cached per pass")
-    p.add_argument("--algo", default="walk", choices=["chunk", "walk"], help="order-free walk kernel")
-    p.add_argument("--chunk-walks", type=int, default=8, help="walks per chunk for --algo chunk")
     p.add_argument("--file-order", action="store_true", help="start the walks in root order instead of hub-neighbourhoods first")
     p.add_argument("--no-depth1", dest="depth1", action="store_false",
                    help="disable the per-(root, depth-1 child) CDF reuse (csrc/walk.cu: step1_cdf_kernel)")
@@ -340,8 +338,7 @@ def run_b200(args):
 
     hg, emb_h, roots, d = make_inputs(args, rank)
     dg = G.DeviceGraph(hg, dev)
-    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, algo=args.algo, chunk_walks=args.chunk_walks,
-                         depth1=args.depth1, hub_first=not args.file_order)
+    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, depth1=args.depth1, hub_first=not args.file_order)
     emb = S.pad_embedding(emb_h, dev)
     bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
     t0 = time.time()
@@ -459,11 +456,11 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(roots_pin.numel() * 4),
                     "d2h_bytes_per_step": int(3 * 2 * W * 4 + 8),
                     "call": "WalkSampler.run + finalize + emit_d_rows with pinned host roots in / rows out"},
-            "gpu_launches": ((9 if smp.depth1 and args.algo == "walk" else 7) if reuse else 5) * args.steps,
+            "gpu_launches": ((9 if smp.depth1 else 7) if reuse else 5) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "K1 stage: gg::hub_score_kernel + gg::root_cdf_kernel + gg_walk_sample (%sgg::walk_kernel) (ld=%d)" % (
-                             "gg::root_step_kernel + gg::step1_cdf_kernel + " if smp.depth1 and args.algo == "walk" else "", ld),
+                             "gg::root_step_kernel + gg::step1_cdf_kernel + " if smp.depth1 else "", ld),
                          "kernel_ms": k_ms, "precompute_ms": pre_ms, "walk_kernel_ms": walk_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "bytes_per_neg_edge": alg_bytes / max(c0["accepted"], 1),
@@ -482,11 +479,9 @@ def run_b200(args):
                                           ("cyc_enum", "cyc_score", "cyc_choose", "cyc_step0", "cyc_step1", "cyc_step2p")}},
         }
         if not args.no_cpu_baseline and world >= 1:
-            par_dev = trees.parent
-
             def parent_rows(rs):   # reuse the GPU-built trees (checked against the oracle BFS in tests/)
                 idx = np.searchsorted(roots, rs)
-                return par_dev[torch.as_tensor(idx, device=dev)].cpu().numpy()
+                return trees.parent_arrays(torch.as_tensor(idx, device=dev)).cpu().numpy()
             ref = CpuReference(hg, emb_h, roots, args.cpu_seconds, 1, parent_rows=parent_rows)
             line["cpu_baseline"] = ref.run(args.seed)[0]
             ref.close()

@@ -10,6 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgraphgan_b200.so")
+STAMP = LIB + ".hash"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -21,12 +22,25 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def source_hash():
+    """sha256 over every file the library is built from (names + contents) and the compiler flags."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    for p in deps:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def stale():
-    if not os.path.exists(LIB):
+    """True when the .so is missing or was built from other sources than the ones in the tree (content hash in a
+    sidecar file, so that copying the tree -- which changes mtimes -- does not trigger rebuilds)."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
-    return any(os.path.getmtime(p) > t for p in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def nvcc_path():
@@ -46,6 +60,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + out.stdout)
     if verbose:
         print(out.stdout)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

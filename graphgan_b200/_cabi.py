@@ -9,6 +9,7 @@ import os
 from . import _build
 
 _LIB = None
+ABI_VERSION = 2      # == GG_ABI_VERSION of include/graphgan_b200.h
 
 
 class GGError(RuntimeError):
@@ -20,7 +21,8 @@ class WalkDesc(C.Structure):
     _fields_ = [
         ("n_node", C.c_int64), ("ld", C.c_int32),
         ("emb", C.c_void_p), ("bias", C.c_void_p), ("indptr", C.c_void_p), ("adj", C.c_void_p),
-        ("n_roots", C.c_int64), ("roots", C.c_void_p), ("parent", C.c_void_p), ("walk_ptr", C.c_void_p),
+        ("n_roots", C.c_int64), ("roots", C.c_void_p), ("tree_bits", C.c_void_p), ("tree_words", C.c_int64),
+        ("walk_ptr", C.c_void_p),
         ("n_walks", C.c_int64), ("for_d", C.c_int32), ("rng_mode", C.c_int32), ("d1_bits", C.c_void_p),
         ("seed", C.c_uint64), ("pass_tag", C.c_uint32), ("max_path", C.c_int32),
         ("stream", C.c_void_p), ("n_stream", C.c_int64), ("update_ratio", C.c_double),
@@ -29,8 +31,7 @@ class WalkDesc(C.Structure):
         ("wsuml", C.c_void_p), ("paths", C.c_void_p), ("path_len", C.c_void_p), ("counters", C.c_void_p),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64), ("work_counter", C.c_void_p),
         ("edge_score", C.c_void_p), ("root_q", C.c_void_p), ("rq_ptr", C.c_void_p),
-        ("hub_threshold", C.c_int32), ("chunk_walks", C.c_int32),
-        ("chunk_ptr", C.c_void_p), ("n_chunks", C.c_int64), ("walk_slot", C.c_void_p),
+        ("hub_threshold", C.c_int32), ("reserved2", C.c_int32), ("walk_slot", C.c_void_p),
         ("s1_nq", C.c_int64), ("s1_slot", C.c_void_p), ("s1_ptr", C.c_void_p), ("s1_cnt", C.c_void_p), ("s1_n", C.c_void_p),
         ("s1_q", C.c_void_p), ("s1_ids", C.c_void_p), ("first_idx", C.c_void_p), ("s1_order", C.c_void_p), ("walk_order", C.c_void_p),
     ]
@@ -48,7 +49,9 @@ SIGNATURES = {
     "gg_walk_finalize": (C.c_int, [_I64, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gg_emit_d_rows": (C.c_int, [_I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gg_bfs_scratch_bytes": (C.c_int, [_I64, _I64, C.POINTER(_I64)]),
-    "gg_bfs_build": (C.c_int, [_I64, _I64, _P, _P, _I64, _P, _P, _P, _I64, _P]),
+    "gg_tree_words": (C.c_int, [_I64, C.POINTER(_I64)]),
+    "gg_bfs_build": (C.c_int, [_I64, _I64, _P, _P, _I64, _P, _P, _I64, _P, _I64, _P]),
+    "gg_tree_parent": (C.c_int, [_I64, _P, _P, _I64, _P, _P, _I64, _P, _P]),
     "gg_pair_reward": (C.c_int, [_I64, _P, _P, _P, _P, _I32, _P, _P]),
     "gg_all_score": (C.c_int, [_I64, _P, _P, _I32, _P, _P]),
     "gg_pair_grad": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P]),
@@ -70,11 +73,13 @@ def lib():
     global _LIB
     if _LIB is None:
         path = _build.LIB
-        if not os.path.exists(path):
+        if _build.stale():      # missing, or built from other sources than the tree holds (content hash)
+            if os.path.exists(path) and _build.nvcc_path() is None:
+                raise GGError("libgraphgan_b200.so was built from different sources and there is no nvcc to rebuild it")
             try:
                 _build.build()
             except Exception as e:  # noqa: BLE001
-                raise GGError("libgraphgan_b200.so is missing and could not be built: %s" % e) from e
+                raise GGError("libgraphgan_b200.so is missing or stale and could not be built: %s" % e) from e
         try:
             handle = C.CDLL(path)
         except OSError as e:
@@ -85,7 +90,7 @@ def lib():
             except AttributeError as e:
                 raise GGError("libgraphgan_b200.so does not export %s (stale build?)" % name) from e
             fn.restype, fn.argtypes = res, args
-        if handle.gg_abi_version() != 1:
+        if handle.gg_abi_version() != ABI_VERSION:
             raise GGError("ABI version mismatch")
         _LIB = handle
     return _LIB

@@ -1,25 +1,32 @@
 // bfs.cu -- BFS-tree construction for a batch of roots (sm_100a).
 //
-// Replaces GraphGAN.construct_trees (reference src/GraphGAN/graph_gan.py:84-108).  The
-// reference stores, per root, a dict node -> [father, children...]: O(N) Python objects per
-// root and O(N^2) overall, which cannot exist at N >= 1e5.  Here a tree is one int32 parent
-// array; the children of `cur` are recovered during the walk as the adjacency entries whose
-// father is `cur`, which reproduces the reference's list order exactly (graph_gan.py:102-105).
+// Replaces GraphGAN.construct_trees (reference src/GraphGAN/graph_gan.py:84-108).  The reference stores, per
+// root, a dict node -> [father, children...]: O(N) Python objects per root and O(N^2) overall, which cannot exist
+// at N >= 1e5.  Here a tree is ONE BIT PER WALK-CSR ENTRY: bit e of the root's row is set iff adj[e] is a child of
+// the entry's source node in that root's tree.  The walk reads those bits next to adj[] / edge_score[] (contiguous,
+// no per-neighbour probe), and the children of a node come out in adjacency order == the reference's list order
+// (graph_gan.py:102-105).  The father of a node is never stored: the walk only descends, so it is the previous node.
 //
-// The father of v must be the FIRST node, in the reference's FIFO order, that has v in its
-// adjacency.  Level-synchronous formulation: number every (frontier node, adjacency slot)
-// pair of a level consecutively in (frontier order, slot order) -- that number `q` is exactly
-// the order in which the reference's loop would look at the edge -- and let every edge whose
-// head is still undiscovered atomicMin its q into claim[head].  The minimum is the reference's
-// discoverer, and the winners in q order (a stable compaction) are the next frontier in FIFO
-// order.  q keeps growing across levels, so a stale claim can never equal a current q.
+// Semantics to reproduce: the father of v is the FIRST node, in the reference's FIFO order, that has v in its
+// adjacency.  Since every node occurs at most once in an adjacency list of the walk CSR, "first" is decided by the
+// queue position of the father alone.  Level-synchronous, one 1024-thread CTA per root, everything random lives
+// in SHARED memory:
 //
-// One 1024-thread CTA owns one root at a time.  Per level: (A) prefix sums over the frontier,
-// (B) claim sweep, (C) winner sweep (records one win bit per frontier edge), (D) prefix sum of
-// the winner counts, (E) scatter from the win bits.  Small frontier nodes (degree <= 32) are
-// processed one per thread, large ones one per warp.  A visited bitmap in SHARED memory (N bits;
-// global scratch when N > ~1.7M) filters already-discovered heads, so the only random global
-// accesses are one atomicMin + one 4-byte read per edge into the NEXT level.
+//   * the visited bitmap (N bits) sits in shared memory (global scratch only when N > ~1.2 M);
+//   * the level's frontier is consumed in CHUNKS of consecutive queue entries holding <= 8192 adjacency entries,
+//     8 consecutive entries per thread (one 32-B sector);
+//   * inside a chunk, several frontier nodes may reach the same undiscovered node: every candidate entry proposes
+//     key = (chunk-local index of its source, tag of the head) with atomicMin into a 16 k-slot shared table indexed
+//     by the head's low bits.  After a barrier the slot's minimum decides: same key -> this entry is THE tree edge;
+//     same head, other key -> an earlier father won; other head -> hash collision, the entry stays pending and the
+//     round repeats (rare: the table is at most half full).  Earlier chunks have already set their winners' visited
+//     bits, so "first in queue order" holds across chunks as well;
+//   * winners are compacted in entry order (a block scan) = FIFO order, appended to the queue, and their bits are
+//     OR-ed into the root's tree row.
+//
+// The only global traffic is the adjacency stream (shared by all roots, L2), the queue (4 N bytes per root, written
+// and read once, sequentially) and the tree row itself.  No per-root claim / parent / offset arrays (the round-1
+// builder kept 32 N bytes of them per concurrent root and was bound by random DRAM sectors).
 // HBM/L2-bound integer work; no tensor cores.
 #include "gg_common.cuh"
 
@@ -27,259 +34,270 @@ namespace gg {
 namespace {
 
 constexpr int BFS_THREADS = 1024;
-constexpr int BFS_WARPS = BFS_THREADS / 32;
-constexpr long long BFS_SMEM_BITMAP_MAX_BYTES = 200 * 1024;
+constexpr int BFS_EPT = 8;                                 // adjacency entries per thread per slab
+constexpr unsigned BFS_SLAB = BFS_THREADS * BFS_EPT;       // 8192 entries
+constexpr int BFS_HBITS = 14;
+constexpr unsigned BFS_HSLOTS = 1u << BFS_HBITS;           // 16384 slots, 64 KB
+constexpr unsigned BFS_EMPTY = 0xffffffffu;
+// shared memory: table | start[1025] | a0[1024] | warp totals[32] | pad | bitmap
+constexpr unsigned BFS_FIXED_WORDS = BFS_HSLOTS + (BFS_THREADS + 1) + BFS_THREADS + 32 + 31;
+constexpr long long BFS_SMEM_MAX_BYTES = 227 * 1024;
+constexpr long long BFS_SMEM_BITMAP_MAX_BYTES = BFS_SMEM_MAX_BYTES - 4ll * BFS_FIXED_WORDS;
 
-__host__ __device__ inline long long bfs_words_per_cta(long long n, long long nnz, bool bitmap_in_smem) {
-    const long long bm = bitmap_in_smem ? 0 : (n + 31) / 32;
-    return 8 * n + nnz / 32 + bm + 8;
-}
-
-// exclusive scan of f(i), i in [0,n), into out[0..n]; returns total (block-wide, all threads).
-// Every warp scans one contiguous chunk with a running carry (coalesced, no block barrier inside the loop);
-// the 32 chunk totals are scanned once; a second sweep adds the chunk offsets.  Three barriers in total --
-// the frontier of a level can have ~N entries, and a barrier per 1024 elements used to dominate the build.
-template <typename F>
-__device__ unsigned block_exclusive_scan(F f, unsigned *out, unsigned n, unsigned *s_warp, unsigned *s_carry) {
+// inclusive block scan (1024 threads); `total` = sum over the block.  Ends with a barrier, so s_tot may be reused.
+__device__ __forceinline__ unsigned block_scan_incl(unsigned v, unsigned *s_tot, unsigned &total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned chunk = ((n + BFS_WARPS - 1) / BFS_WARPS + 31u) & ~31u;
-    const unsigned lo = wid * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
-    unsigned carry = 0;
-    for (unsigned base = lo; base < hi; base += 32) {
-        const unsigned i = base + lane;
-        const unsigned v = (i < hi) ? f(i) : 0u;
-        unsigned x = v;
+    unsigned x = v;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned y = __shfl_up_sync(FULL, x, off);
-            if (lane >= off) x += y;
-        }
-        if (i < hi) out[i] = carry + x - v;
-        carry += __shfl_sync(FULL, x, 31);
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned y = __shfl_up_sync(FULL, x, off);
+        if (lane >= off) x += y;
     }
-    if (lane == 0) s_warp[wid] = carry;
+    if (lane == 31) s_tot[wid] = x;
     __syncthreads();
     if (wid == 0) {
-        const unsigned v = s_warp[lane];
-        unsigned t = v;
+        unsigned t = s_tot[lane];
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const unsigned y = __shfl_up_sync(FULL, t, off);
             if (lane >= off) t += y;
         }
-        s_warp[lane] = t - v;                 // exclusive offset of every chunk
-        if (lane == 31) *s_carry = t;         // grand total
+        s_tot[lane] = t;
     }
     __syncthreads();
-    const unsigned add = s_warp[wid];
-    if (add)
-        for (unsigned i = lo + lane; i < hi; i += 32) out[i] += add;
-    const unsigned total = *s_carry;
-    if (threadIdx.x == 0) out[n] = total;
+    const unsigned add = wid ? s_tot[wid - 1] : 0u;
+    total = s_tot[31];
     __syncthreads();
-    return total;
+    return x + add;
 }
 
-__global__ void __launch_bounds__(BFS_THREADS, 1)
-bfs_kernel(long long n_node, long long nnz, const long long *__restrict__ indptr, const int *__restrict__ adj,
-           long long n_roots, const int *__restrict__ roots, int *__restrict__ parent, unsigned *__restrict__ scratch,
-           int bitmap_in_smem) {
-    extern __shared__ unsigned s_bitmap[];
-    __shared__ unsigned s_warp[32];
-    __shared__ unsigned s_carry, s_nbig;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t N = (size_t)n_node;
-    const size_t bm_words = (N + 31) / 32;
-    unsigned *claim = scratch + (size_t)blockIdx.x * (size_t)bfs_words_per_cta(n_node, nnz, bitmap_in_smem != 0);
-    int *fa = reinterpret_cast<int *>(claim + N);
-    int *fb = fa + N;
-    unsigned *off = reinterpret_cast<unsigned *>(fb + N);   // [N+1] q numbering
-    unsigned *base = off + N + 1;                            // [N+1] winners per frontier node / compaction offsets
-    unsigned *woff = base + N + 1;                           // [N+1] first win-mask word of a frontier node
-    unsigned *wmask = woff + N + 1;                          // [nnz/32 + N + 1]
-    unsigned *big = wmask + nnz / 32 + N + 1;                // [N] frontier indices of nodes with degree > 32
-    unsigned *bm = bitmap_in_smem ? s_bitmap : (big + N);
+template <bool VSMEM>
+__device__ __forceinline__ bool v_test(const unsigned *V, int w) {
+    const unsigned word = VSMEM ? V[w >> 5] : __ldcg(V + (w >> 5));
+    return (word >> (w & 31)) & 1u;
+}
 
+template <bool VSMEM>
+__global__ void __launch_bounds__(BFS_THREADS, 1)
+bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__restrict__ adj, long long n_roots,
+           const int *__restrict__ roots, uint32_t *__restrict__ tree_bits, long long tree_words, int *__restrict__ qbuf,
+           unsigned *__restrict__ gbitmap, int tagbits) {
+    extern __shared__ __align__(16) unsigned bfs_smem[];
+    unsigned *table = bfs_smem;
+    unsigned *start = table + BFS_HSLOTS;                  // [1025] exclusive prefix of the chunk's degrees
+    unsigned *a0s = start + BFS_THREADS + 1;               // [1024] first walk-CSR entry of the chunk's nodes
+    unsigned *s_tot = a0s + BFS_THREADS;                   // [32]
+    const size_t bm_words = ((size_t)n_node + 31) / 32;
+    unsigned *V = VSMEM ? (s_tot + 32 + 31) : (gbitmap + (size_t)blockIdx.x * bm_words);
+    int *Q = qbuf + (size_t)blockIdx.x * (size_t)n_node;
+    const int tid = threadIdx.x;
+    const unsigned tagmask = (tagbits >= 32) ? 0xffffffffu : ((1u << tagbits) - 1u);
+
+    for (unsigned s = tid; s < BFS_HSLOTS; s += BFS_THREADS) table[s] = BFS_EMPTY;
     for (long long r = blockIdx.x; r < n_roots; r += gridDim.x) {
         const int root = roots[r];
-        int *par = parent + (size_t)r * N;
-        for (size_t i = threadIdx.x; i < N; i += BFS_THREADS) { claim[i] = 0xffffffffu; par[i] = -1; }
-        for (size_t i = threadIdx.x; i < bm_words; i += BFS_THREADS) bm[i] = 0u;
+        uint32_t *tb = tree_bits + (size_t)r * (size_t)tree_words;
+        for (long long i = tid; i < tree_words; i += BFS_THREADS) tb[i] = 0u;
+        for (size_t i = tid; i < bm_words; i += BFS_THREADS) V[i] = 0u;
         __syncthreads();
-        if (threadIdx.x == 0) { bm[root >> 5] |= 1u << (root & 31); fa[0] = root; }
+        if (tid == 0) { V[root >> 5] = 1u << (root & 31); Q[0] = root; }
         __syncthreads();
-        unsigned nf = 1, level_base = 1;
-        int *cur = fa, *nxt = fb;
-        while (nf > 0) {
-            // A: q numbering and win-mask word numbering = prefix sums over the frontier
-            const unsigned n_edges = block_exclusive_scan(
-                [&](unsigned i) { const int u = cur[i]; return (unsigned)(indptr[u + 1] - indptr[u]); }, off, nf, s_warp,
-                &s_carry);
-            block_exclusive_scan(
-                [&](unsigned i) { const int u = cur[i]; return (unsigned)((indptr[u + 1] - indptr[u] + 31) >> 5); }, woff, nf,
-                s_warp, &s_carry);
-            // Work assignment (per sweep): a frontier node of degree <= 32 is handled by ONE THREAD (32 nodes
-            // per warp advance in parallel -- most nodes of a power-law graph are small, and a warp per node would
-            // spend its time on the dependent cur -> indptr -> adj latency chain); larger nodes are collected in
-            // `big` during sweep B and handled by a whole warp, 128 edges in flight.
-            if (threadIdx.x == 0) s_nbig = 0;
-            __syncthreads();
-            // B: every frontier edge with an undiscovered head claims it with its visit order
-            for (unsigned i = threadIdx.x; i < nf; i += BFS_THREADS) {
-                const int u = cur[i];
-                const long long a0 = indptr[u];
-                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
-                if (dg > 32) { big[atomicAdd(&s_nbig, 1u)] = i; continue; }
-                for (unsigned j0 = 0; j0 < dg; j0 += 8) {   // 8 independent adjacency loads in flight per thread
-                    int v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = (j0 + k < dg) ? __ldg(adj + a0 + j0 + k) : -1;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (v[k] >= 0 && !((bm[v[k] >> 5] >> (v[k] & 31)) & 1u)) atomicMin(claim + v[k], q0 + j0 + k);
+        unsigned lo = 0, hi = 1, tail = 1;
+        while (lo < hi) {                                   // one BFS level: queue entries [lo, hi)
+            for (unsigned i = lo; i < hi;) {
+                // ---- window: the next <= 1024 frontier nodes; the chunk = the longest prefix with <= SLAB entries
+                const unsigned idx = i + tid;
+                unsigned a = 0, deg = 0;
+                if (idx < hi) {
+                    const int u = Q[idx];
+                    const long long b0 = indptr[u];
+                    a = (unsigned)b0; deg = (unsigned)(indptr[u + 1] - b0);
                 }
-            }
-            __syncthreads();
-            const unsigned nbig = s_nbig;
-            for (unsigned b = wid; b < nbig; b += BFS_WARPS) {
-                const unsigned i = big[b];
-                const int u = cur[i];
-                const long long a0 = indptr[u];
-                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
-                for (unsigned j0 = 0; j0 < dg; j0 += 128) {
-                    int v[4];
+                unsigned tot;
+                const unsigned incl = block_scan_incl(deg, s_tot, tot);
+                unsigned m = (unsigned)__syncthreads_count(idx < hi && incl <= BFS_SLAB);   // incl is non-decreasing
+                if (m == 0) m = 1;                          // one node with more than SLAB entries: a chunk of its own
+                if ((unsigned)tid < m) { start[tid] = incl - deg; a0s[tid] = a; }
+                if ((unsigned)tid == m - 1) start[m] = incl;
+                __syncthreads();
+                const unsigned E = start[m];
+                const bool single = (m == 1);               // a node's own entries never collide: no table needed
+                for (unsigned s0 = 0; s0 < E; s0 += BFS_SLAB) {
+                    const unsigned k0 = s0 + (unsigned)tid * BFS_EPT;
+                    unsigned j0 = 0;
+                    if (!single && k0 < E) {                // owner of entry k0: last j with start[j] <= k0
+                        unsigned l = 0, h = m - 1;
+                        while (l < h) {
+                            const unsigned mid = (l + h + 1) >> 1;
+                            if (start[mid] <= k0) l = mid; else h = mid - 1;
+                        }
+                        j0 = l;
+                    }
+                    unsigned ee[BFS_EPT], key[BFS_EPT];
+                    int w[BFS_EPT];
+                    {
+                        unsigned jj = j0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { const unsigned j = j0 + 32 * k + lane; v[k] = (j < dg) ? __ldg(adj + a0 + j) : -1; }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (v[k] >= 0 && !((bm[v[k] >> 5] >> (v[k] & 31)) & 1u)) atomicMin(claim + v[k], q0 + j0 + 32 * k + lane);
-                }
-            }
-            __syncthreads();
-            // C: winners per frontier node, one win bit per edge
-            for (unsigned i = threadIdx.x; i < nf; i += BFS_THREADS) {
-                const int u = cur[i];
-                const long long a0 = indptr[u];
-                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i];
-                if (dg > 32) continue;
-                unsigned mk = 0;
-                for (unsigned j0 = 0; j0 < dg; j0 += 8) {
-                    int v[8];
-                    unsigned cl[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = (j0 + k < dg) ? __ldg(adj + a0 + j0 + k) : -1;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        cl[k] = (v[k] >= 0 && !((bm[v[k] >> 5] >> (v[k] & 31)) & 1u)) ? __ldcg(claim + v[k]) : 0u;   // q >= 1
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (cl[k] == q0 + j0 + k) mk |= 1u << (j0 + k);
-                }
-                if (dg) wmask[woff[i]] = mk;
-                base[i] = __popc(mk);
-            }
-            for (unsigned b = wid; b < nbig; b += BFS_WARPS) {
-                const unsigned i = big[b];
-                const int u = cur[i];
-                const long long a0 = indptr[u];
-                const unsigned dg = (unsigned)(indptr[u + 1] - a0), q0 = level_base + off[i], w0 = woff[i];
-                unsigned c = 0;
-                for (unsigned j0 = 0; j0 < dg; j0 += 128) {
-                    int v[4];
-                    bool cand[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { const unsigned j = j0 + 32 * k + lane; v[k] = (j < dg) ? __ldg(adj + a0 + j) : -1; }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) cand[k] = v[k] >= 0 && !((bm[v[k] >> 5] >> (v[k] & 31)) & 1u);
-                    unsigned cl[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) cl[k] = cand[k] ? __ldcg(claim + v[k]) : 0u;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const unsigned mk = __ballot_sync(FULL, cand[k] && cl[k] == q0 + j0 + 32 * k + lane);
-                        if (j0 + 32 * k < dg) {
-                            if (lane == 0) wmask[w0 + (j0 >> 5) + k] = mk;
-                            c += __popc(mk);
+                        for (int x = 0; x < BFS_EPT; ++x) {
+                            const unsigned k = k0 + x;
+                            ee[x] = 0xffffffffu; key[x] = 0;
+                            if (k < E) {
+                                while (jj + 1 < m && start[jj + 1] <= k) ++jj;
+                                ee[x] = a0s[jj] + (k - start[jj]);
+                                key[x] = jj << tagbits;
+                            }
                         }
                     }
-                }
-                if (lane == 0) base[i] = c;
-            }
-            __syncthreads();
-            // D: stable compaction offsets
-            const unsigned n_next = block_exclusive_scan([&](unsigned i) { return base[i]; }, base, nf, s_warp, &s_carry);
-            // E: winners become children (father = u) and the next frontier, in q order
-            for (unsigned i = threadIdx.x; i < nf; i += BFS_THREADS) {
-                unsigned o = base[i];
-                if (base[i + 1] == o) continue;   // no winner under this node
-                const int u = cur[i];
-                const long long a0 = indptr[u];
-                const unsigned dg = (unsigned)(indptr[u + 1] - a0);
-                if (dg > 32) continue;
-                unsigned mk = wmask[woff[i]];
-                while (mk) {
-                    const int j = __ffs(mk) - 1;
-                    mk &= mk - 1u;
-                    const int v = __ldg(adj + a0 + j);
-                    nxt[o++] = v;
-                    par[v] = u;
-                    atomicOr(bm + (v >> 5), 1u << (v & 31));
-                }
-            }
-            for (unsigned b = wid; b < nbig; b += BFS_WARPS) {
-                const unsigned i = big[b];
-                unsigned o = base[i];
-                if (base[i + 1] == o) continue;
-                const int u = cur[i];
-                const long long a0 = indptr[u];
-                const unsigned dg = (unsigned)(indptr[u + 1] - a0), w0 = woff[i];
-                for (unsigned j0 = 0; j0 < dg; j0 += 32) {
-                    const unsigned mk = wmask[w0 + (j0 >> 5)];
-                    if (mk == 0u) continue;
-                    if ((mk >> lane) & 1u) {
-                        const int v = __ldg(adj + a0 + j0 + lane);
-                        nxt[o + __popc(mk & ((1u << lane) - 1u))] = v;
-                        par[v] = u;
-                        atomicOr(bm + (v >> 5), 1u << (v & 31));
+#pragma unroll
+                    for (int x = 0; x < BFS_EPT; ++x) w[x] = (ee[x] != 0xffffffffu) ? __ldg(adj + ee[x]) : -1;
+                    unsigned cm = 0;                        // candidate entries: head not discovered yet
+#pragma unroll
+                    for (int x = 0; x < BFS_EPT; ++x)
+                        if (w[x] >= 0 && !v_test<VSMEM>(V, w[x])) cm |= 1u << x;
+                    unsigned wm = 0;                        // winners: the tree edges among my entries
+                    if (single) {
+                        wm = cm;
+#pragma unroll
+                        for (int x = 0; x < BFS_EPT; ++x)
+                            if ((cm >> x) & 1u) atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < BFS_EPT; ++x) key[x] |= ((unsigned)w[x] >> BFS_HBITS) & tagmask;
+                        unsigned pend = cm;
+                        for (;;) {
+#pragma unroll
+                            for (int x = 0; x < BFS_EPT; ++x)
+                                if ((pend >> x) & 1u) atomicMin(table + ((unsigned)w[x] & (BFS_HSLOTS - 1)), key[x]);
+                            __syncthreads();
+                            unsigned still = 0;
+#pragma unroll
+                            for (int x = 0; x < BFS_EPT; ++x) {
+                                if (!((pend >> x) & 1u)) continue;
+                                const unsigned t = table[(unsigned)w[x] & (BFS_HSLOTS - 1)];
+                                if (t == key[x]) {
+                                    wm |= 1u << x;
+                                    atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
+                                } else if ((t & tagmask) != (key[x] & tagmask)) {
+                                    still |= 1u << x;       // the slot went to another head: try again
+                                }
+                            }
+                            const int any = __syncthreads_or(still != 0u);
+#pragma unroll
+                            for (int x = 0; x < BFS_EPT; ++x)
+                                if ((pend >> x) & 1u) table[(unsigned)w[x] & (BFS_HSLOTS - 1)] = BFS_EMPTY;
+                            pend = still;
+                            if (!any) break;
+                            __syncthreads();
+                        }
                     }
-                    o += __popc(mk);
+                    // ---- winners in entry order = FIFO order: append to the queue, set their tree bits
+                    unsigned ntot;
+                    const unsigned cnt = (unsigned)__popc(wm);
+                    unsigned off = tail + block_scan_incl(cnt, s_tot, ntot) - cnt;
+                    unsigned word = 0xffffffffu, mask = 0;
+#pragma unroll
+                    for (int x = 0; x < BFS_EPT; ++x) {
+                        if (!((wm >> x) & 1u)) continue;
+                        Q[off++] = w[x];
+                        const unsigned wi = ee[x] >> 5;
+                        if (wi != word) {
+                            if (mask) atomicOr(tb + word, mask);
+                            word = wi; mask = 0;
+                        }
+                        mask |= 1u << (ee[x] & 31);
+                    }
+                    if (mask) atomicOr(tb + word, mask);
+                    tail += ntot;
                 }
+                i += m;
             }
-            __syncthreads();
-            level_base += n_edges;
-            nf = n_next;
-            int *t = cur; cur = nxt; nxt = t;
+            __syncthreads();                                // the queue entries appended above are read next
+            lo = hi; hi = tail;
         }
-        __syncthreads();
     }
+}
+
+// tree row -> parent array (tests / compatibility): parent[adj[e]] = source(e) for every set bit e
+__global__ void tree_parent_kernel(long long n_node, const long long *__restrict__ indptr, const int *__restrict__ adj,
+                                   long long n_roots, const uint32_t *__restrict__ tree_bits, long long tree_words,
+                                   int *__restrict__ parent) {
+    const long long r = blockIdx.y;
+    const uint32_t *tb = tree_bits + (size_t)r * (size_t)tree_words;
+    int *par = parent + (size_t)r * (size_t)n_node;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n_node; u += (long long)gridDim.x * blockDim.x) {
+        const long long a0 = indptr[u], a1 = indptr[u + 1];
+        for (long long e = a0; e < a1; ++e)
+            if ((tb[e >> 5] >> (e & 31)) & 1u) par[adj[e]] = (int)u;
+    }
+}
+
+int bfs_tagbits(long long n_node) {
+    int bits = 0;
+    while (bits < 40 && (1ll << bits) < n_node) ++bits;     // ids < 2^bits
+    return bits > BFS_HBITS ? bits - BFS_HBITS : 0;
 }
 
 }  // namespace
 }  // namespace gg
 
+extern "C" int gg_tree_words(int64_t nnz, int64_t *words) {
+    GG_REQUIRE(words && nnz >= 0, "bad arguments");
+    *words = (nnz + 31) / 32 + 1;
+    return 0;
+}
+
 extern "C" int gg_bfs_scratch_bytes(int64_t n_node, int64_t nnz, int64_t *bytes) {
     GG_REQUIRE(bytes && n_node >= 0 && nnz >= 0, "bad arguments");
-    const bool in_smem = (n_node + 31) / 32 * 4 <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
-    *bytes = (int64_t)gg::sm_count() * gg::bfs_words_per_cta(n_node, nnz, in_smem) * 4;
+    const long long bm_bytes = (n_node + 31) / 32 * 4;
+    const bool in_smem = bm_bytes <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
+    *bytes = (int64_t)gg::sm_count() * (4 * n_node + (in_smem ? 0 : bm_bytes)) + 16;
     return 0;
 }
 
 extern "C" int gg_bfs_build(int64_t n_node, int64_t nnz, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
-                            const int32_t *roots, int32_t *parent, void *scratch, int64_t scratch_bytes, void *stream) {
-    GG_REQUIRE(indptr && adj && roots && parent && scratch, "null pointer");
-    GG_REQUIRE(nnz < 0xfffffff0ll, "too many edges for 32-bit visit numbers");
+                            const int32_t *roots, uint32_t *tree_bits, int64_t tree_words, void *scratch,
+                            int64_t scratch_bytes, void *stream) {
+    GG_REQUIRE(indptr && adj && roots && tree_bits && scratch, "null pointer");
+    GG_REQUIRE(nnz < 0x7ffffff0ll, "too many adjacency entries for 32-bit entry numbers");
+    GG_REQUIRE(tree_words >= (nnz + 31) / 32, "tree_words too small (gg_tree_words)");
     if (n_roots == 0 || n_node == 0) return 0;
     const long long bm_bytes = (n_node + 31) / 32 * 4;
     const bool in_smem = bm_bytes <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
-    const int64_t per_cta = gg::bfs_words_per_cta(n_node, nnz, in_smem) * 4;
+    const int64_t per_cta = 4 * n_node + (in_smem ? 0 : bm_bytes);
     int64_t ctas = scratch_bytes / per_cta;
     if (ctas > gg::sm_count()) ctas = gg::sm_count();
     if (ctas > n_roots) ctas = n_roots;
     GG_REQUIRE(ctas >= 1, "scratch too small");
-    const size_t smem = in_smem ? (size_t)bm_bytes : 0;
-    if (smem > 48 * 1024)
-        GG_CHECK(cudaFuncSetAttribute(gg::bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gg::bfs_kernel<<<(unsigned)ctas, gg::BFS_THREADS, smem, (cudaStream_t)stream>>>(
-        n_node, nnz, (const long long *)indptr, adj, n_roots, roots, parent, (unsigned *)scratch, in_smem ? 1 : 0);
+    const int tagbits = gg::bfs_tagbits(n_node);
+    GG_REQUIRE(tagbits + 10 <= 31, "graph too large for the 32-bit proposal keys");
+    int *qbuf = (int *)scratch;
+    unsigned *gbm = in_smem ? nullptr : (unsigned *)(qbuf + (size_t)ctas * (size_t)n_node);
+    const size_t smem = 4 * (size_t)gg::BFS_FIXED_WORDS + (in_smem ? (size_t)bm_bytes : 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_smem) {
+        GG_CHECK(cudaFuncSetAttribute(gg::bfs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gg::bfs_kernel<true><<<(unsigned)ctas, gg::BFS_THREADS, smem, st>>>(
+            n_node, (const long long *)indptr, adj, n_roots, roots, tree_bits, tree_words, qbuf, gbm, tagbits);
+    } else {
+        GG_CHECK(cudaFuncSetAttribute(gg::bfs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gg::bfs_kernel<false><<<(unsigned)ctas, gg::BFS_THREADS, smem, st>>>(
+            n_node, (const long long *)indptr, adj, n_roots, roots, tree_bits, tree_words, qbuf, gbm, tagbits);
+    }
     return gg::check_cuda(cudaGetLastError(), "bfs kernel launch");
+}
+
+extern "C" int gg_tree_parent(int64_t n_node, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
+                              const int32_t *roots, const uint32_t *tree_bits, int64_t tree_words, int32_t *parent,
+                              void *stream) {
+    GG_REQUIRE(indptr && adj && tree_bits && parent, "null pointer");
+    (void)roots;
+    if (n_roots == 0 || n_node == 0) return 0;
+    GG_REQUIRE(n_roots <= 65535, "at most 65535 roots per call");
+    cudaStream_t st = (cudaStream_t)stream;
+    GG_CHECK(cudaMemsetAsync(parent, 0xff, sizeof(int32_t) * (size_t)n_roots * (size_t)n_node, st));
+    long long bx = (n_node + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    gg::tree_parent_kernel<<<dim3((unsigned)bx, (unsigned)n_roots), 256, 0, st>>>(
+        n_node, (const long long *)indptr, adj, n_roots, tree_bits, tree_words, parent);
+    return gg::check_cuda(cudaGetLastError(), "tree parent kernel launch");
 }

@@ -35,43 +35,61 @@ struct Rng {
     }
 };
 
-// children of `cur` among its adjacency entries [a0, a1): U tiles of 32 entries in flight per iteration
+// children of `cur` among its walk-CSR entries [a0, a1): the set bits of the root's tree row `tb` (csrc/bfs.cu), in
+// entry order == adjacency order == the reference's list order (graph_gan.py:102-105).  One coalesced load brings 32
+// bitmap words (1024 entries); only words with a set bit touch adj[] / edge_score[], U of them in flight.
 template <int U>
-__device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const int32_t *__restrict__ par, int cur,
-                                                   long long a0, long long a1, bool cached, int *ids, float *sc, int lane,
-                                                   int &n, float &m) {
+__device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const uint32_t *__restrict__ tb, long long a0,
+                                                   long long a1, bool cached, int *ids, float *sc, int lane, int &n, float &m) {
+    if (a1 <= a0) return;
     const unsigned lt = (1u << lane) - 1u;
-    for (long long e0 = a0; e0 < a1; e0 += 32 * U) {
-        int v[U], p[U];
-        float cs[U];
+    const long long wfirst = a0 >> 5, wlast = (a1 - 1) >> 5;
+    for (long long wb = wfirst; wb <= wlast; wb += 32) {
+        const long long wi = wb + lane;
+        unsigned word = (wi <= wlast) ? __ldg(tb + wi) : 0u;
+        if (wi == wfirst) word &= 0xffffffffu << (a0 & 31);
+        if (wi == wlast && (a1 & 31)) word &= (1u << (a1 & 31)) - 1u;
+        unsigned nz = __ballot_sync(FULL, word != 0u);
+        while (nz) {
+            int jw[U], v[U];
+            unsigned wv[U];
+            float cs[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const long long e = e0 + 32 * k + lane;
-            v[k] = (e < a1) ? __ldg(d.adj + e) : -1;
-            cs[k] = (cached && e < a1) ? __ldg(d.edge_score + e) : 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k) p[k] = (v[k] >= 0) ? __ldg(par + v[k]) : -2;
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            if (e0 + 32 * k >= a1) break;   // warp-uniform: short adjacency lists use one tile
-            const bool isc = p[k] == cur;
-            const unsigned mk = __ballot_sync(FULL, isc);
-            if (isc) {
-                const int pos = n + __popc(mk & lt);
-                ids[pos] = v[k];
-                if (cached) { sc[pos] = cs[k]; m = fmaxf(m, cs[k]); }
+            for (int k = 0; k < U; ++k) {
+                jw[k] = nz ? (__ffs(nz) - 1) : -1;
+                nz &= nz - 1u;                              // 0 & 0xffffffff == 0: stays empty
             }
-            n += __popc(mk);
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const unsigned x = __shfl_sync(FULL, word, jw[k] & 31);
+                wv[k] = (jw[k] >= 0) ? x : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const bool isc = (wv[k] >> lane) & 1u;
+                const long long e = ((wb + jw[k]) << 5) + lane;
+                v[k] = isc ? __ldg(d.adj + e) : -1;
+                cs[k] = (cached && isc) ? __ldg(d.edge_score + e) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if (jw[k] < 0) break;                       // warp-uniform
+                if ((wv[k] >> lane) & 1u) {
+                    const int pos = n + __popc(wv[k] & lt);
+                    ids[pos] = v[k];
+                    if (cached) { sc[pos] = cs[k]; m = fmaxf(m, cs[k]); }
+                }
+                n += __popc(wv[k]);
+            }
         }
     }
 }
 
-// Candidate list of `cur` in the tree of the root whose parent array is `par` (graph_gan.py:250-259):
+// Candidate list of `cur` in the tree of the root whose tree row is `tb` (graph_gan.py:250-259):
 // [father] + children in adjacency order, with scores all_score[cur, cand] (generator.py:21) -- cached hub
 // scores or the on-demand canonical dot -- and their max.  Warp-cooperative; results are warp-uniform.
 template <int CPL>
-__device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t *__restrict__ par, int cur, int prev,
+__device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t *__restrict__ tb, int cur, int prev,
                                            bool inc_father, int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
                                            int &n_out, float &m_out, int *&ids_out, float *&sc_out,
                                            unsigned long long &rows_gathered, unsigned int (&cyc)[7]) {
@@ -84,7 +102,7 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t 
     float m = -INFINITY;   // running max of the cached scores (lane local)
     const long long t_e = clock64();
     // (16 tiles in flight for hub adjacency was measured: the extra registers spill and the kernel gets slower)
-    enumerate_children<UNR>(d, par, cur, a0, a1, cached, ids, sc, lane, n, m);
+    enumerate_children<UNR>(d, tb, a0, a1, cached, ids, sc, lane, n, m);
     __syncwarp();
     const long long t_s = clock64();
     cyc[0] += (unsigned int)(t_s - t_e);
@@ -102,7 +120,7 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const int32_t 
         m = warp_max(m);
         if (inc_father) m = fmaxf(m, sc[0]);
     } else {
-        m = list_max<false>(sc, n, lane);
+        m = list_max(sc, n, lane);
     }
     m_out = m;
     cyc[1] += (unsigned int)(clock64() - t_s);
@@ -119,7 +137,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
                                         unsigned long long &overflow, unsigned long long &rows_gathered,
                                         unsigned int (&cyc)[7]) {
     const int root = d.roots[slot];
-    const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
+    const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
     int cur = root, prev = -1, step = 0, fedge = -1, plen = 0;
     int steps = 0, suml = 0, status = GG_NOTRUN, sample = -1;
     int32_t *prow = (d.max_path > 0 && d.paths) ? d.paths + (size_t)w * (size_t)d.max_path : nullptr;
@@ -163,14 +181,14 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             if (d.for_d && step == 1) inc_father = false;
             if (!d.for_d && step == 1 && ((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u)) inc_father = false;
             int *ids; float *sc; float m;
-            build_list<CPL>(d, par, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
+            build_list<CPL>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
             if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
 
             // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
             const long long t_c = clock64();
             const double u = rng.draw((uint32_t)root, k, (uint32_t)step);   // the stream mode consumes it regardless
             if (rng.exhausted) { status = GG_NOTRUN; break; }
-            idx = (n == 1) ? 0 : choose_index<false>(sc, n, m, u, lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
+            idx = (n == 1) ? 0 : choose_index(sc, n, m, u, lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
             nxt = ids[idx];
             __syncwarp();
             cyc[2] += (unsigned int)(clock64() - t_c);
@@ -265,12 +283,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) step1_cdf_kernel(const 
         if (__ldg(d.s1_cnt + pos) < S1_MIN_WALKS) continue;   // a pair picked once is cheaper inside its walk (no CDF array)
         const int slot = __ldg(d.s1_slot + pos);
         const int root = d.roots[slot];
-        const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
+        const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
         const long long e = d.indptr[root] + (pos - __ldg(d.rq_ptr + slot));
         const int c = __ldg(d.adj + e);
         const bool inc_father = !d.for_d && !((d.d1_bits[e >> 5] >> (e & 31)) & 1u);   // graph_gan.py:258-259
         int n; float m; int *ids; float *sc;
-        build_list<CPL>(d, par, c, root, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
+        build_list<CPL>(d, tb, c, root, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
         if (lane == 0) d.s1_n[pos] = n;
         if (n == 0) continue;
         const long long o = __ldg(d.s1_ptr + pos);
@@ -330,150 +348,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_kernel(const __gri
         }
         walk_one<CPL>(d, rng, slot, k, w, s_ids, s_sc, g_ids, g_sc, lane, raw_steps, raw_suml, overflow, rows_gathered,
                       cyc);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < 7; ++q) if (cyc[q]) atomicAdd(d.counters + GG_CNT_CYC_ENUM + q, (unsigned long long)cyc[q]);
-        if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
-        if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
-        if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
-        if (rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
-    }
-}
-
-// ---------------------------------------------------------------- chunked order-free kernel
-// One warp owns a CHUNK of up to 32 walks of the same root (lane <-> walk for the bookkeeping) and advances
-// them together: walks of the chunk that stand on the same node share ONE candidate list / softmax / CDF
-// (the heavy, warp-cooperative part) and only differ in their uniform draw.  With sample_num = deg(root)
-// walks per root and a peaked softmax most walks of a chunk share their first nodes, which removes most of
-// the redundant list constructions; the draws stay keyed by (root, walk, step), so results are unchanged.
-constexpr int RUNNING = -1;
-
-template <int CPL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_chunk_kernel(const __grid_constant__ gg_walk_desc d) {
-    extern __shared__ __align__(16) unsigned char walk_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
-    int *s_ids = reinterpret_cast<int *>(s_sc + SC_CAP);
-    const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
-    int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
-    float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
-    const uint32_t k0key = (uint32_t)d.seed, k1key = (uint32_t)(d.seed >> 32);
-    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
-    unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
-    const bool ratio_all = d.update_ratio >= 1.0;
-
-    for (;;) {
-        unsigned int item = 0;
-        if (lane == 0) item = atomicAdd(d.work_counter, 1u);
-        item = __shfl_sync(FULL, item, 0);
-        if ((long long)item >= d.n_chunks) break;
-        const long long t_walk = clock64();
-        long long lo = 0, hi = d.n_roots;   // chunk -> root slot: last slot with chunk_ptr[slot] <= item
-        while (hi - lo > 1) {
-            const long long mid = (lo + hi) >> 1;
-            if (__ldg(d.chunk_ptr + mid) <= (long long)item) lo = mid; else hi = mid;
-        }
-        const int slot = (int)lo;
-        const long long w0 = __ldg(d.walk_ptr + slot), nw = __ldg(d.walk_ptr + slot + 1) - w0;
-        const int cw = d.chunk_walks;
-        const long long kbase = ((long long)item - __ldg(d.chunk_ptr + slot)) * cw;
-        const int cnt = (int)((nw - kbase) < cw ? (nw - kbase) : cw);
-        const bool mine = lane < cnt;
-        const uint32_t k = (uint32_t)(kbase + lane);
-        const long long w = w0 + kbase + lane;
-        const int root = d.roots[slot];
-        const int32_t *par = d.parent + (size_t)slot * (size_t)d.n_node;
-        int32_t *prow = (mine && d.max_path > 0 && d.paths) ? d.paths + (size_t)w * (size_t)d.max_path : nullptr;
-        if (!ratio_all) {  // graph_gan.py:189/209: one draw per root
-            uint32_t a, b;
-            philox4x32_10((uint32_t)root, 0xffffffffu, 0u, d.pass_tag, k0key, k1key, a, b);
-            if (!(u53(a, b) < d.update_ratio)) {
-                if (mine) {
-                    d.samples[w] = -1; d.status[w] = GG_SKIPPED; d.first_edge[w] = -1; d.wsteps[w] = 0; d.wsuml[w] = 0;
-                    if (d.path_len) d.path_len[w] = 0;
-                }
-                continue;
-            }
-        }
-        int cur = root, prev = -1, step = 0, fedge = -1, steps = 0, suml = 0, plen = 1, sample = -1;
-        int status = mine ? RUNNING : GG_NOTRUN;
-        if (prow) prow[0] = root;
-        const long long a0r = d.indptr[root], a1r = d.indptr[root + 1];
-        if (d.root_q) {   // root step: every lane inverts the root's precomputed CDF for its own walk
-            const long long t0 = clock64();
-            const int n0 = (int)(a1r - a0r);
-            if (n0 == 0) {
-                if (mine) status = GG_VOID;   // graph_gan.py:252-253
-            } else if (mine) {
-                uint32_t a, b;
-                philox4x32_10((uint32_t)root, k, 0u, d.pass_tag, k0key, k1key, a, b);
-                const int idx = cdf_search(d.root_q + __ldg(d.rq_ptr + slot), n0, u53(a, b));
-                const int nxt = __ldg(d.adj + a0r + idx);
-                fedge = (int)(a0r + idx);
-                if (prow && plen < d.max_path) prow[plen] = nxt;
-                plen = 2; steps = 1; suml = n0; prev = root; cur = nxt; step = 1;
-            }
-            __syncwarp();
-            cyc[3] += (unsigned int)(clock64() - t0);
-        }
-        for (;;) {
-            const unsigned running = __ballot_sync(FULL, status == RUNNING);
-            if (!running) break;
-            const long long t_step = clock64();
-            const int leader = __ffs(running) - 1;
-            const int ccur = __shfl_sync(FULL, cur, leader), cstep = __shfl_sync(FULL, step, leader);
-            const int cprev = __shfl_sync(FULL, prev, leader), cfedge = __shfl_sync(FULL, fedge, leader);
-            const unsigned grp = __ballot_sync(FULL, status == RUNNING && cur == ccur);
-            bool inc_father = cstep > 0;
-            if (d.for_d && cstep == 1) inc_father = false;
-            if (!d.for_d && cstep == 1 && ((d.d1_bits[cfedge >> 5] >> (cfedge & 31)) & 1u)) inc_father = false;
-            int n; float m; int *ids; float *sc;
-            build_list<CPL>(d, par, ccur, cprev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
-            if (n == 0) {   // graph_gan.py:252-257
-                if ((grp >> lane) & 1u) status = GG_VOID;
-            } else {
-                const long long t_c = clock64();
-                float S = 1.0f;
-                double car[2] = {1.0, 0.0}, total = 1.0;
-                if (n > 1) {
-                    S = softmax_exp_sum<false>(sc, n, m, lane);
-                    total = cdf_total<false>(sc, n, S, lane, car);
-                }
-                const long long a0c = d.indptr[ccur];
-                for (unsigned rest = grp; rest; rest &= rest - 1u) {
-                    const int j = __ffs(rest) - 1;
-                    const uint32_t kj = __shfl_sync(FULL, k, j);
-                    uint32_t a, b;
-                    philox4x32_10((uint32_t)root, kj, (uint32_t)cstep, d.pass_tag, k0key, k1key, a, b);
-                    const int idx = (n == 1) ? 0 : cdf_pick<false>(sc, n, S, total, u53(a, b), lane, car);
-                    const int nxt = ids[idx];
-                    if (lane == j) {
-                        if (cstep == 0) fedge = (int)(a0c + idx);
-                        if (prow && plen < d.max_path) prow[plen] = nxt;
-                        ++plen; ++steps; suml += n;
-                        if (inc_father && idx == 0) { sample = cur; status = GG_DONE; }   // graph_gan.py:264-266
-                        else { prev = cur; cur = nxt; ++step; }
-                    }
-                }
-                __syncwarp();
-                cyc[2] += (unsigned int)(clock64() - t_c);
-            }
-            cyc[cstep == 0 ? 3 : (cstep == 1 ? 4 : 5)] += (unsigned int)(clock64() - t_step);
-        }
-        if (mine) {
-            d.samples[w] = sample; d.status[w] = status; d.first_edge[w] = fedge; d.wsteps[w] = steps; d.wsuml[w] = suml;
-            if (d.path_len) d.path_len[w] = (status == GG_DONE) ? plen : 0;
-            raw_steps += (unsigned)steps; raw_suml += (unsigned)suml;
-            if (status == GG_DONE && d.max_path > 0 && plen > d.max_path) overflow += 1;
-        }
-        cyc[6] += (unsigned int)(clock64() - t_walk);
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        raw_steps += __shfl_xor_sync(FULL, raw_steps, off);
-        raw_suml += __shfl_xor_sync(FULL, raw_suml, off);
-        overflow += __shfl_xor_sync(FULL, overflow, off);
     }
     if (lane == 0) {
 #pragma unroll
@@ -631,7 +505,8 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
     const gg_walk_desc &d = *dp;
     GG_REQUIRE(d.ld > 0 && d.ld % 32 == 0, "ld must be a positive multiple of 32");
     if (d.n_walks == 0 || d.n_roots == 0) return 0;   // nothing to do (empty batches carry null pointers)
-    GG_REQUIRE(d.emb && d.bias && d.indptr && d.adj && d.roots && d.parent && d.walk_ptr, "null graph/embedding pointer");
+    GG_REQUIRE(d.emb && d.bias && d.indptr && d.adj && d.roots && d.tree_bits && d.walk_ptr, "null graph/embedding pointer");
+    GG_REQUIRE(d.tree_words > 0, "tree_words missing (gg_tree_words)");
     GG_REQUIRE(d.samples && d.status && d.first_edge && d.wsteps && d.wsuml && d.counters && d.work_counter,
                "null output pointer");
     GG_REQUIRE(d.for_d || d.d1_bits, "G mode needs d1_bits");
@@ -681,24 +556,6 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
 #undef GG_S1
             GG_CHECK(cudaGetLastError());
             GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));   // the walk kernel's queue starts at 0
-        }
-        if (d.chunk_ptr) {
-            GG_REQUIRE(d.n_chunks >= 0 && d.n_chunks < (1ll << 32), "bad chunk count");
-            GG_REQUIRE(d.chunk_walks >= 1 && d.chunk_walks <= 32, "chunk_walks must be in [1, 32]");
-            if (d.n_chunks == 0) return 0;
-#define GG_CHUNK(C)                                                                                                   \
-    GG_CHECK(cudaFuncSetAttribute(gg::walk_chunk_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                  gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                      \
-    gg::walk_chunk_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d)
-            switch (cpl) {
-                case 1: GG_CHUNK(1); break;
-                case 2: GG_CHUNK(2); break;
-                case 4: GG_CHUNK(4); break;
-                case 8: GG_CHUNK(8); break;
-                default: gg::set_error("gg_walk_sample: unsupported ld %d (supported: 32, 64, 128, 256)", d.ld); return 2;
-            }
-#undef GG_CHUNK
-            return gg::check_cuda(cudaGetLastError(), "walk chunk kernel launch");
         }
         switch (cpl) {
 #define GG_WALK(C)                                                                                                    \

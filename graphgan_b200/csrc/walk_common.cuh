@@ -88,36 +88,29 @@ __device__ __forceinline__ void score_edges(const float *__restrict__ emb, const
     __syncwarp();
 }
 
-// The score buffer is either this warp's shared-memory slice or its global scratch (generic pointer).  An
-// LDS/STS specialisation of the shared path was measured (round 1) and was not faster than generic LD/ST, so
-// the SH template parameter is kept only as a hook.
-template <bool SH> __device__ __forceinline__ float buf_ld(const float *p, int i) { return p[i]; }
-template <bool SH> __device__ __forceinline__ void buf_st(float *p, int i, float v) { p[i] = v; }
-
 // max over sc[0..n)
-template <bool SH>
 __device__ __forceinline__ float list_max(const float *sc, int n, int lane) {
     float m = -INFINITY;
-    for (int i = lane; i < n; i += 32) m = fmaxf(m, buf_ld<SH>(sc, i));
+    for (int i = lane; i < n; i += 32) m = fmaxf(m, sc[i]);
     return warp_max(m);
 }
 
 // softmax numerators in place (sc[i] <- e_i = exp_c(s_i - m)) and their canonical sum
 // S = T_0 + T_1 + ... (tile sums by butterfly; 0 + T_0 == T_0 and S + 0 == S exactly, so empty
 // tiles of the unrolled tail are harmless).  UNR tiles are in flight per iteration.
-template <bool SH, int U = UNR>
+template <int U = UNR>
 __device__ __forceinline__ float softmax_exp_sum(float *sc, int n, float m, int lane) {
     float S = 0.0f;
     for (int t0 = 0; t0 < n; t0 += 32 * U) {
         float x[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int i = t0 + 32 * u + lane; x[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
+        for (int u = 0; u < U; ++u) { const int i = t0 + 32 * u + lane; x[u] = (i < n) ? sc[i] : 0.0f; }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (t0 + 32 * u >= n) break;            // warp-uniform: no work for the empty tiles of a short list
             const int i = t0 + 32 * u + lane;
             float e = 0.0f;
-            if (i < n) { e = exp_c(__fsub_rn(x[u], m)); buf_st<SH>(sc, i, e); }
+            if (i < n) { e = exp_c(__fsub_rn(x[u], m)); sc[i] = e; }
             S = __fadd_rn(S, warp_sum_butterfly(e));
         }
     }
@@ -127,14 +120,14 @@ __device__ __forceinline__ float softmax_exp_sum(float *sc, int n, float m, int 
 
 // total of the float64 CDF over p_i = e_i / S.  Lane (t & 31) also keeps the running total after tile t
 // in car[t >> 5] (tiles 0..63), so that the draw can jump straight to the tile that contains it.
-template <bool SH, int U = UNR>
+template <int U = UNR>
 __device__ __forceinline__ double cdf_total(const float *sc, int n, float S, int lane, double (&car)[2]) {
     double total = 0.0;
     car[0] = car[1] = 0.0;
     for (int t0 = 0; t0 < n; t0 += 32 * U) {
         float e[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? buf_ld<SH>(sc, i) : 0.0f; }
+        for (int u = 0; u < U; ++u) { const int i = t0 + 32 * u + lane; e[u] = (i < n) ? sc[i] : 0.0f; }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (t0 + 32 * u >= n) break;            // warp-uniform
@@ -149,12 +142,11 @@ __device__ __forceinline__ double cdf_total(const float *sc, int n, float S, int
 }
 
 // first i with cdf_i / total > u, scanning tiles [t_begin, ...) with `carry` = CDF before tile t_begin
-template <bool SH>
 __device__ __forceinline__ int cdf_pick_from(const float *sc, int n, float S, double total, double u, int lane,
                                              int t_begin, double carry) {
     for (int t0 = 32 * t_begin; t0 < n; t0 += 32) {
         const int i = t0 + lane;
-        double x = (double)__fdiv_rn((i < n) ? buf_ld<SH>(sc, i) : 0.0f, S);
+        double x = (double)__fdiv_rn((i < n) ? sc[i] : 0.0f, S);
         x = warp_scan_ks(x, lane);
         const double q = __ddiv_rn(__dadd_rn(carry, x), total);
         const unsigned hit = __ballot_sync(FULL, (i < n) && (q > u));
@@ -166,7 +158,6 @@ __device__ __forceinline__ int cdf_pick_from(const float *sc, int n, float S, do
 
 // The CDF is non-decreasing, so the first index with q > u lies in the first tile whose LAST q exceeds u,
 // and that last q is exactly car[t] / total (same operations as the linear scan performs).  All lanes return idx.
-template <bool SH>
 __device__ __forceinline__ int cdf_pick(const float *sc, int n, float S, double total, double u, int lane,
                                         const double (&car)[2]) {
     const int ntiles = (n + 31) >> 5;
@@ -181,7 +172,7 @@ __device__ __forceinline__ int cdf_pick(const float *sc, int n, float S, double 
     if (t_hit < 0) {   // beyond the 64 tracked tiles (n > 2048): linear scan from tile 64
         if (ntiles <= 64) return n - 1;
         const double c63 = __shfl_sync(FULL, car[1], 31);
-        return cdf_pick_from<SH>(sc, n, S, total, u, lane, 64, c63);
+        return cdf_pick_from(sc, n, S, total, u, lane, 64, c63);
     }
     double before = 0.0;
     if (t_hit > 0) {
@@ -189,7 +180,7 @@ __device__ __forceinline__ int cdf_pick(const float *sc, int n, float S, double 
         const double lo = __shfl_sync(FULL, car[0], tp & 31), hi = __shfl_sync(FULL, car[1], tp & 31);
         before = (tp >> 5) ? hi : lo;
     }
-    return cdf_pick_from<SH>(sc, n, S, total, u, lane, t_hit, before);
+    return cdf_pick_from(sc, n, S, total, u, lane, t_hit, before);
 }
 
 // softmax + CDF + draw over sc[0..n) given its max m (== ggo_choose).  All lanes return the index.
@@ -223,51 +214,37 @@ __device__ __forceinline__ int cdf_pick_tiles(const float *sc, int n, float S, d
         const unsigned mk = __ballot_sync(FULL, p);
         if (mk) {
             const int t_hit = tb + __ffs(mk) - 1;
-            return cdf_pick_from<false>(sc, n, S, total, u, lane, t_hit, t_hit > 0 ? tiles[t_hit - 1] : 0.0);
+            return cdf_pick_from(sc, n, S, total, u, lane, t_hit, t_hit > 0 ? tiles[t_hit - 1] : 0.0);
         }
     }
     return n - 1;
 }
 
-template <bool SH>
 __device__ __forceinline__ int choose_index(float *sc, int n, float m, double u, int lane, double *tiles = nullptr) {
     float S;
     double car[2], total;
     if (n > SC_CAP && tiles && ((n + 31) >> 5) <= SC_CAP / 2) {
         // the list lives in global scratch: 16 tiles in flight per pass, per-tile totals in shared memory
-        S = softmax_exp_sum<SH, 16>(sc, n, m, lane);
+        S = softmax_exp_sum<16>(sc, n, m, lane);
         total = cdf_total_tiles(sc, n, S, lane, tiles);
         return cdf_pick_tiles(sc, n, S, total, u, lane, tiles);
     }
     if (n > SC_CAP) {
-        S = softmax_exp_sum<SH, 16>(sc, n, m, lane);
-        total = cdf_total<SH, 16>(sc, n, S, lane, car);
+        S = softmax_exp_sum<16>(sc, n, m, lane);
+        total = cdf_total<16>(sc, n, S, lane, car);
     } else {
-        S = softmax_exp_sum<SH>(sc, n, m, lane);
-        total = cdf_total<SH>(sc, n, S, lane, car);
+        S = softmax_exp_sum(sc, n, m, lane);
+        total = cdf_total(sc, n, S, lane, car);
     }
-    return cdf_pick<SH>(sc, n, S, total, u, lane, car);
+    return cdf_pick(sc, n, S, total, u, lane, car);
 }
 
 // normalised CDF q_i = cdf_i / total written out (the array numpy's choice would searchsorted)
-__device__ __forceinline__ void cdf_store_m(float *sc, int n, float m, double *q_out, int lane) {
-    const float S = softmax_exp_sum<false>(sc, n, m, lane);
-    double car[2];
-    const double total = cdf_total<false>(sc, n, S, lane, car);
-    double carry = 0.0;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-        const int i = t0 + lane;
-        double x = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;
-        x = warp_scan_ks(x, lane);
-        if (i < n) q_out[i] = __ddiv_rn(__dadd_rn(carry, x), total);
-        carry = __dadd_rn(carry, __shfl_sync(FULL, x, 31));
-    }
-}
 __device__ __forceinline__ void cdf_store(float *sc, int n, double *q_out, int lane) {
-    const float m = list_max<false>(sc, n, lane);
-    const float S = softmax_exp_sum<false>(sc, n, m, lane);
+    const float m = list_max(sc, n, lane);
+    const float S = softmax_exp_sum(sc, n, m, lane);
     double car[2];
-    const double total = cdf_total<false>(sc, n, S, lane, car);
+    const double total = cdf_total(sc, n, S, lane, car);
     double carry = 0.0;
     for (int t0 = 0; t0 < n; t0 += 32) {
         const int i = t0 + lane;
@@ -281,7 +258,7 @@ __device__ __forceinline__ void cdf_store(float *sc, int n, double *q_out, int l
 // un-normalised CDF c_i = carry + scan(e/S)_i written out, the total after the n entries (c[n] = total).  One scan
 // pass: the division by the total is left to the search, which performs it only on the entries it probes.
 __device__ __forceinline__ void cdf_store_raw(float *sc, int n, float m, double *c_out, int lane) {
-    const float S = softmax_exp_sum<false>(sc, n, m, lane);
+    const float S = softmax_exp_sum(sc, n, m, lane);
     double carry = 0.0;
     for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
         double x[UNR];

@@ -77,6 +77,13 @@ class HostGraph:
         """graph[i] exactly as the reference holds it."""
         return self.raw_adj[self.raw_indptr[i]:self.raw_indptr[i + 1]]
 
+    def __getitem__(self, i):
+        """``graph[i]`` as reference-style code indexes it (graph_gan.py:190: ``pos = self.graph[i]``)."""
+        return self.neighbors(int(i)).tolist()
+
+    def __len__(self):
+        return self.n_node
+
     def degrees(self):
         """len(graph[i]) == sample_num of prepare_data_for_d (graph_gan.py:190-191)."""
         return np.diff(self.raw_indptr)

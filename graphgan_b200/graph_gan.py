@@ -66,7 +66,7 @@ class GraphGAN(object):
         self.trees, self._tree_key = None, None
         import torch.distributed as _d
         if not (_d.is_available() and _d.is_initialized() and _d.get_world_size() > 1) and \
-                4 * self.n_node * self.n_node <= config.tree_cache_bytes:
+                self._tree_bytes(self.n_node) <= config.tree_cache_bytes:
             print("constructing BFS-trees...")
             self.trees = self.construct_trees(self.root_nodes)
 
@@ -89,6 +89,10 @@ class GraphGAN(object):
             self._dp_d, self._dp_g = DataParallelStep(self.discriminator), DataParallelStep(self.generator)
 
     # ------------------------------------------------------------------ trees (graph_gan.py:63-108)
+    def _tree_bytes(self, n_roots):
+        """device bytes of the tree rows of `n_roots` roots: one bit per walk-CSR entry each (csrc/bfs.cu)"""
+        return n_roots * 4 * ((int(self.host_graph.adj.shape[0]) + 31) // 32 + 1)
+
     def construct_trees(self, nodes):
         """BFS trees of ``nodes`` -> sampler.TreeBatch (parent arrays on the GPU)."""
         return self.sampler.build_trees(np.asarray(nodes, np.int32))
@@ -110,10 +114,11 @@ class GraphGAN(object):
             from .parallel import balanced_root_ranges
             lo, hi = balanced_root_ranges(self.host_graph.degrees()[roots] + 1, self.world)[self.rank]
             roots = roots[lo:hi]
-            if self.trees is not None and self._tree_key != (lo, hi):
+            key = (lo, hi, hash(roots.tobytes()))           # the cached trees belong to exactly these roots
+            if self.trees is not None and self._tree_key != key:
                 self.trees = None
-            if self.trees is None and 4 * self.n_node * max(hi - lo, 1) <= config.tree_cache_bytes:
-                self.trees, self._tree_key = self.construct_trees(roots), (lo, hi)
+            if self.trees is None and self._tree_bytes(max(hi - lo, 1)) <= config.tree_cache_bytes:
+                self.trees, self._tree_key = self.construct_trees(roots), key
             if self.trees is not None:
                 yield self.trees
                 return
@@ -288,15 +293,34 @@ class GraphGAN(object):
 
     # ------------------------------------------------------------------ checkpoint (tf.train.Saver stand-in)
     def save(self, path):
-        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-        self.torch.save({"generator": self.generator.state_dict(), "discriminator": self.discriminator.state_dict(),
-                         "d1_bits": self.device_graph.d1_bits.cpu(), "pass_counter": self.pass_counter,
-                         "shuffle_rng": self.shuffle_rng.get_state()}, path)
+        """Replicas are bit-identical, so rank 0 alone writes (to a temporary file, then an atomic rename).  The
+        father-removal bits (graph_gan.py:258-259) are per root, i.e. per rank shard: they are OR-reduced over the
+        ranks first, so the file holds the removals of every root."""
+        torch = self.torch
+        bits = self.device_graph.d1_bits.clone()
+        if self.dist:
+            self.dist.all_reduce(bits, op=self.dist.ReduceOp.BOR)
+        if self.rank == 0:
+            os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+            rs = self.shuffle_rng.get_state()
+            state = {"generator": self.generator.state_dict(), "discriminator": self.discriminator.state_dict(),
+                     "d1_bits": bits.cpu(), "pass_counter": torch.tensor(self.pass_counter),
+                     "shuffle_rng": {"keys": torch.from_numpy(rs[1].astype(np.int64)), "pos": int(rs[2]),
+                                     "has_gauss": int(rs[3]), "cached_gaussian": float(rs[4])}}
+            tmp = "%s.tmp.%d" % (path, os.getpid())
+            torch.save(state, tmp)
+            os.replace(tmp, path)
+        if self.dist:
+            self.dist.barrier()
 
     def load(self, path):
-        sd = self.torch.load(path, weights_only=False)
+        """Every rank reads the same file; the OR-ed removal bits only add bits for roots of other shards, which this
+        rank's walks never look at."""
+        sd = self.torch.load(path, weights_only=True, map_location="cpu")
         self.generator.load_state_dict(sd["generator"])
         self.discriminator.load_state_dict(sd["discriminator"])
         self.device_graph.d1_bits.copy_(sd["d1_bits"].to(self.device))
-        self.pass_counter = sd["pass_counter"]
-        self.shuffle_rng.set_state(sd["shuffle_rng"])
+        self.pass_counter = int(sd["pass_counter"])
+        r = sd["shuffle_rng"]
+        self.shuffle_rng.set_state(("MT19937", r["keys"].numpy().astype(np.uint32), r["pos"], r["has_gauss"],
+                                    r["cached_gaussian"]))

@@ -39,11 +39,35 @@ def pad_embedding(emb, device=None):
 
 
 class TreeBatch:
-    """BFS trees of a batch of roots as parent arrays: ``trees[root]`` of graph_gan.py:84-108."""
+    """BFS trees of a batch of roots (``trees[root]`` of graph_gan.py:84-108) as one bit per walk-CSR entry:
+    bit e of row k <=> adj[e] is a child of entry e's source node in the tree of roots[k] (csrc/bfs.cu)."""
 
-    def __init__(self, roots, parent):
-        self.roots = roots      # device int32 [R]
-        self.parent = parent    # device int32 [R, N]
+    def __init__(self, roots, tree_bits, graph=None):
+        self.roots = roots            # device int32 [R]
+        self.tree_bits = tree_bits    # device int32 [R, tree_words] (bit patterns)
+        self.graph = graph
+
+    def slice(self, lo, hi):
+        return TreeBatch(self.roots[lo:hi].contiguous(), self.tree_bits[lo:hi].contiguous(), self.graph)
+
+    def select(self, idx):
+        return TreeBatch(self.roots[idx].contiguous(), self.tree_bits[idx].contiguous(), self.graph)
+
+    def parent_arrays(self, rows=None):
+        """int32 [R', N] parent arrays (root and unreachable nodes: -1) of all / the selected rows -- the form the
+        oracle and host-side consumers use; expanded on the device by gg_tree_parent."""
+        import torch
+        g, lib = self.graph, _cabi.lib()
+        bits = self.tree_bits if rows is None else self.tree_bits[rows].contiguous()
+        roots = self.roots if rows is None else self.roots[rows].contiguous()
+        R = int(bits.shape[0])
+        out = torch.empty((R, g.n_node), dtype=torch.int32, device=bits.device)
+        st = torch.cuda.current_stream(bits.device).cuda_stream
+        for lo in range(0, R, 32768):
+            hi = min(R, lo + 32768)
+            _cabi.check(lib.gg_tree_parent(g.n_node, ptr(g.indptr), ptr(g.adj), hi - lo, ptr(roots[lo:hi]), ptr(bits[lo:hi]),
+                                           int(bits.shape[1]), ptr(out[lo:hi]), st), "gg_tree_parent")
+        return out
 
 
 class WalkOutput:
@@ -76,10 +100,6 @@ class WalkPlan:
         nw = self.walk_ptr[1:] - self.walk_ptr[:-1]
         self.walk_slot = torch.repeat_interleave(torch.arange(R, dtype=torch.int32, device=dev), nw,
                                                  output_size=self.n_walks) if self.n_walks else None
-        self.chunk_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
-        cw = sampler.chunk_walks
-        self.chunk_ptr[1:] = torch.cumsum((nw + cw - 1) // cw, 0)              # chunks of <= cw walks of one root
-        self.n_chunks = int(self.chunk_ptr[-1].item())
         r = trees.roots.long()
         self.rq_ptr = torch.zeros(R + 1, dtype=torch.int64, device=dev)
         self.rq_ptr[1:] = torch.cumsum(g.indptr[r + 1] - g.indptr[r], 0)       # prefix of the roots' walk degrees
@@ -104,7 +124,7 @@ class WalkPlan:
     def start_order(self, sampler):
         """Order in which walk_kernel starts the walks: roots whose neighbourhood holds the largest hub first
         (a walk that steps onto a 10 k-neighbour node costs ~100x a median one; started last it would be the
-        tail of the launch), walks of one root kept together (they share the parent array in L2).  Static per
+        tail of the launch), walks of one root kept together (they share the tree row in L2).  Static per
         plan; plumbing only (one gather, one segment max, one sort)."""
         if self._order is None and self.n_walks > 0 and self.nq > 0:
             torch, g, dev = sampler.torch, sampler.g, sampler.device
@@ -142,7 +162,7 @@ class WalkPlan:
 
 
 class WalkSampler:
-    def __init__(self, graph, hub_threshold=128, algo="walk", chunk_walks=8, depth1=True, hub_first=True):
+    def __init__(self, graph, hub_threshold=128, depth1=True, hub_first=True):
         import torch
         self.torch = torch
         self.g = graph
@@ -150,11 +170,6 @@ class WalkSampler:
         self.lib = _cabi.lib()
         self.max_cand = graph.max_deg + 1
         self.hub_threshold = int(hub_threshold)   # 0 disables both per-pass reuses (pure on-demand path)
-        # order-free (Philox) kernel: "walk" = one warp per walk (default, fastest measured); "chunk" = one warp
-        # advances chunk_walks walks of a root together and shares the candidate list of walks on the same node
-        assert algo in ("chunk", "walk")
-        self.algo = algo
-        self.chunk_walks = int(chunk_walks)
         # one CDF per (root, depth-1 child) pair that occurs (needs reuse): the walks of a root that pick the same child
         # share its candidate list (5.5x fewer neighbour probes at step 1 on C3); the builder kernel pulls the pairs
         # from a queue, largest lists first (hub_first), because a 13.8k-entry hub list occupies one warp for ~0.5-1 ms
@@ -175,14 +190,18 @@ class WalkSampler:
         torch = self.torch
         roots_d = roots if isinstance(roots, torch.Tensor) else torch.as_tensor(np.asarray(roots, np.int32)).to(self.device)
         R, N = int(roots_d.shape[0]), self.g.n_node
-        parent = torch.empty((R, N), dtype=torch.int32, device=self.device)
+        nnz = int(self.g.adj.shape[0])
+        words = C.c_int64(0)
+        _cabi.check(self.lib.gg_tree_words(nnz, C.byref(words)), "gg_tree_words")
+        tree_bits = torch.empty((R, words.value), dtype=torch.int32, device=self.device)
         if self._bfs_scratch is None:
             nbytes = C.c_int64(0)
             _cabi.check(self.lib.gg_bfs_scratch_bytes(N, int(self.g.adj.shape[0]), C.byref(nbytes)), "gg_bfs_scratch_bytes")
             self._bfs_scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
-        _cabi.check(self.lib.gg_bfs_build(N, int(self.g.adj.shape[0]), ptr(self.g.indptr), ptr(self.g.adj), R, ptr(roots_d), ptr(parent),
-                                          ptr(self._bfs_scratch), self._bfs_scratch.numel(), self._stream()), "gg_bfs_build")
-        return TreeBatch(roots_d, parent)
+        _cabi.check(self.lib.gg_bfs_build(N, nnz, ptr(self.g.indptr), ptr(self.g.adj), R, ptr(roots_d), ptr(tree_bits),
+                                          words.value, ptr(self._bfs_scratch), self._bfs_scratch.numel(), self._stream()),
+                    "gg_bfs_build")
+        return TreeBatch(roots_d, tree_bits, self.g)
 
     # ------------------------------------------------------------------ K1
     def plan(self, trees, sample_num, for_d, max_path=0):
@@ -194,7 +213,8 @@ class WalkSampler:
         t, d = plan.trees, _cabi.WalkDesc()
         d.n_node, d.ld = self.g.n_node, int(emb.shape[1])
         d.emb, d.bias, d.indptr, d.adj = ptr(emb), ptr(bias), ptr(self.g.indptr), ptr(self.g.adj)
-        d.n_roots, d.roots, d.parent, d.walk_ptr, d.n_walks = plan.n_roots, ptr(t.roots), ptr(t.parent), ptr(plan.walk_ptr), plan.n_walks
+        d.n_roots, d.roots, d.walk_ptr, d.n_walks = plan.n_roots, ptr(t.roots), ptr(plan.walk_ptr), plan.n_walks
+        d.tree_bits, d.tree_words = ptr(t.tree_bits), int(t.tree_bits.shape[1])
         d.for_d, d.rng_mode, d.d1_bits = int(plan.for_d), rng_mode, ptr(self.g.d1_bits)
         d.seed, d.pass_tag, d.max_path = seed, pass_tag, plan.max_path
         d.stream, d.n_stream = (ptr(stream), int(stream.numel())) if stream is not None else (None, 0)
@@ -204,14 +224,12 @@ class WalkSampler:
         d.paths, d.path_len, d.counters = ptr(plan.paths), ptr(plan.path_len), ptr(plan.counters)
         d.scratch, d.scratch_bytes, d.work_counter = ptr(self.scratch), self.scratch.numel(), ptr(self.work_counter)
         d.rq_ptr, d.walk_slot = ptr(plan.rq_ptr), ptr(plan.walk_slot)
-        if self.hub_first and rng_mode == RNG_PHILOX and self.algo == "walk":
+        if self.hub_first and rng_mode == RNG_PHILOX:
             d.walk_order = ptr(plan.start_order(self))
-        if self.algo == "chunk" and rng_mode == RNG_PHILOX:
-            d.chunk_ptr, d.n_chunks, d.chunk_walks = ptr(plan.chunk_ptr), plan.n_chunks, self.chunk_walks
         if reuse:
             self.g.hub_tiles(self.hub_threshold)
             d.edge_score, d.hub_threshold, d.root_q = ptr(self.g.edge_score), self.hub_threshold, ptr(plan.root_q)
-            if self.depth1 and rng_mode == RNG_PHILOX and plan.nq > 0 and plan.n_walks > 0 and self.algo == "walk":
+            if self.depth1 and rng_mode == RNG_PHILOX and plan.nq > 0 and plan.n_walks > 0:
                 b = plan.depth1_buffers(self)
                 d.s1_nq, d.s1_slot, d.s1_ptr, d.s1_cnt, d.s1_n = plan.nq, ptr(b["slot"]), ptr(b["ptr"]), ptr(b["cnt"]), ptr(b["n"])
                 d.s1_q, d.s1_ids, d.first_idx = ptr(b["q"]), ptr(b["ids"]), ptr(b["first"])

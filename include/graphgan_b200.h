@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GG_ABI_VERSION 1
+#define GG_ABI_VERSION 2
 
 /* walk status codes (per walk) */
 enum { GG_NOTRUN = 0, GG_DONE = 1, GG_VOID = 2, GG_SKIPPED = 3 };
@@ -67,7 +67,9 @@ typedef struct gg_walk_desc {
     const int32_t *adj;         /* device [nnz]    */
     int64_t n_roots;
     const int32_t *roots;       /* device [R] root node ids (batch order = reference root order) */
-    const int32_t *parent;      /* device [R, N] BFS fathers (gg_bfs_build); root & unreachable = -1 */
+    const uint32_t *tree_bits;  /* device [R, tree_words] BFS trees (gg_bfs_build): bit e of row k is set iff adj[e]
+                                   is a child of entry e's source node in the tree of roots[k] */
+    int64_t tree_words;         /* row stride of tree_bits in 32-bit words (gg_tree_words(nnz)) */
     const int64_t *walk_ptr;    /* device [R+1] exclusive prefix of per-root sample_num */
     int64_t n_walks;            /* = walk_ptr[R] */
     int32_t for_d;              /* graph_gan.py:225 `for_d` */
@@ -102,12 +104,7 @@ typedef struct gg_walk_desc {
                                    NULL = compute the root step per walk */
     const int64_t *rq_ptr;      /* device [R+1] offsets into root_q (prefix of the roots' walk-CSR degrees) */
     int32_t hub_threshold;
-    int32_t chunk_walks;        /* walks per chunk, 1..32 (with chunk_ptr) */
-    /* optional chunking (GG_RNG_PHILOX only): one warp advances up to 32 walks of a root together and shares
-       the candidate list of walks standing on the same node.  chunk_ptr: device [R+1] exclusive prefix of
-       ceil(sample_num / chunk_walks); NULL = one warp per walk. */
-    const int64_t *chunk_ptr;
-    int64_t n_chunks;
+    int32_t reserved2;
     const int32_t *walk_slot;   /* optional device [W]: root slot of every walk (saves a binary search per walk) */
     /* optional depth-1 reuse (GG_RNG_PHILOX, needs root_q + walk_slot): the walks of a root that pick the same
        depth-1 child share one candidate list.  gg_walk_sample first runs the root step of every walk and counts
@@ -161,13 +158,21 @@ int gg_emit_d_rows(int64_t n_roots, const int32_t *roots, const int64_t *walk_pt
                    int32_t *label, int64_t *n_rows_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
- * Tree construction: GraphGAN.construct_trees (graph_gan.py:84-108) for a batch of roots, as
- * parent arrays (first discoverer in FIFO / adjacency order).  parent: device [R, N].
+ * Tree construction: GraphGAN.construct_trees (graph_gan.py:84-108) for a batch of roots.  A tree is one bit per
+ * walk-CSR entry: bit e of row k is set iff adj[e] is a child of the source node of entry e in the tree of
+ * roots[k] (first discoverer in the reference's FIFO / adjacency order).  tree_bits: device [R, tree_words],
+ * tree_words = gg_tree_words(nnz) (= ceil(nnz / 32) + 1); rows are zeroed by the call.  The walk never needs a
+ * father pointer (it only descends: the father is the previous node); gg_tree_parent expands rows into the
+ * parent-array form (parent[root] = parent[unreachable] = -1) for tests and host-side consumers.
  * ------------------------------------------------------------------------------------------ */
+int gg_tree_words(int64_t nnz, int64_t *words);
 int gg_bfs_scratch_bytes(int64_t n_node, int64_t nnz, int64_t *bytes);
 int gg_bfs_build(int64_t n_node, int64_t nnz, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
-                 const int32_t *roots, int32_t *parent, void *scratch, int64_t scratch_bytes,
-                 void *stream);
+                 const int32_t *roots, uint32_t *tree_bits, int64_t tree_words, void *scratch,
+                 int64_t scratch_bytes, void *stream);
+int gg_tree_parent(int64_t n_node, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
+                   const int32_t *roots, const uint32_t *tree_bits, int64_t tree_words, int32_t *parent,
+                   void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2: pair scoring.  score_k = e_{i_k}.e_{j_k} + b_{j_k} (discriminator.py:21-24 /

@@ -22,7 +22,7 @@ def test_cabi_library_exports_every_declared_symbol():
     assert declared == set(_cabi.SIGNATURES), (declared ^ set(_cabi.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.gg_abi_version() == 1
+    assert lib.gg_abi_version() == _cabi.ABI_VERSION
     # struct layout agreed between ctypes and the header (field count and a few offsets)
     fields = [f[0] for f in _cabi.WalkDesc._fields_]
     struct_src = header[header.index("typedef struct gg_walk_desc"):header.index("} gg_walk_desc;")]
@@ -40,7 +40,7 @@ def test_cabi_argument_errors_do_not_abort():
     assert lib.gg_walk_sample(None, None) != 0
     assert lib.gg_pair_grad(7, 1, 0, None, None, None, None, None, 32, C.c_float(0), None, None, None, None, None, None) != 0
     with pytest.raises(_cabi.GGError):
-        _cabi.check(lib.gg_bfs_build(10, 20, None, None, 1, None, None, None, 0, None), "gg_bfs_build")
+        _cabi.check(lib.gg_bfs_build(10, 20, None, None, 1, None, None, 2, None, 0, None), "gg_bfs_build")
 
 
 def test_product_does_not_import_oracle():

@@ -196,7 +196,7 @@ def test_trainer_epoch_on_cagrqc(cuda_device, tmp_path, monkeypatch):
     # D pass vs canonical oracle
     ce, ne, la = gan.prepare_data_for_d()
     roots = np.arange(5242, dtype=np.int32)
-    par = gan.trees.parent.cpu().numpy()
+    par = gan.trees.parent_arrays().cpu().numpy()
     bits = np.zeros(gan.device_graph.n_bit_words, np.uint32)
     E = can.pad_rows(c.emb_g)
     ref = can.walk_pass(E, np.zeros(5242, np.float32), hg.indptr, hg.adj, roots, par, hg.degrees(), True, bits, seed=5, pass_tag=1)

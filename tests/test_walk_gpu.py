@@ -11,7 +11,7 @@ from tests.golden import loader
 pytestmark = pytest.mark.gpu
 
 
-def _setup(case, cuda_device, roots=None, hub_threshold=256, algo="walk", chunk_walks=32, depth1=True):
+def _setup(case, cuda_device, roots=None, hub_threshold=256, depth1=True):
     import torch
     from graphgan_b200 import graph as G, sampler as S
     from oracle import canonical as can
@@ -24,7 +24,7 @@ def _setup(case, cuda_device, roots=None, hub_threshold=256, algo="walk", chunk_
     indptr, adj = can.unique_csr(case.graph)
     assert np.array_equal(hg.indptr, indptr) and np.array_equal(hg.adj, adj)
     dg = G.DeviceGraph(hg, cuda_device)
-    smp = S.WalkSampler(dg, hub_threshold=hub_threshold, algo=algo, chunk_walks=chunk_walks, depth1=depth1)
+    smp = S.WalkSampler(dg, hub_threshold=hub_threshold, depth1=depth1)
     roots = np.arange(case.n, dtype=np.int32) if roots is None else np.asarray(roots, np.int32)
     trees = smp.build_trees(roots)
     emb = S.pad_embedding(case.emb_g, cuda_device)
@@ -51,7 +51,7 @@ def test_bfs_matches_reference_order(name, cuda_device):
     rs = np.random.RandomState(1)
     roots = np.arange(case.n) if case.n <= 1200 else np.sort(rs.choice(case.n, 600, replace=False))
     hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots)
-    got = trees.parent.cpu().numpy()
+    got = trees.parent_arrays().cpu().numpy()
     want = can.bfs_parents(hg.indptr, hg.adj, roots)
     assert np.array_equal(got, want)
     if "parent" in case:  # the reference's own dict trees (construct_trees) as parent arrays
@@ -60,7 +60,7 @@ def test_bfs_matches_reference_order(name, cuda_device):
 
 def test_bfs_beyond_the_shared_memory_bitmap(cuda_device):
     """N = 1.8 M nodes: the visited bitmap (N bits) no longer fits in shared memory and lives in the per-CTA global
-    scratch (csrc/bfs.cu: bitmap_in_smem = 0).  Same parents as the sequential FIFO BFS, deep sparse trees included
+    scratch (csrc/bfs.cu: bfs_kernel<false>).  Same parents as the sequential FIFO BFS, deep sparse trees included
     (avg degree 3: hundreds of levels of small frontiers)."""
     import torch
     from graphgan_b200 import graph as G, sampler as S, synth
@@ -72,7 +72,7 @@ def test_bfs_beyond_the_shared_memory_bitmap(cuda_device):
     smp = S.WalkSampler(dg)
     roots = synth.pick_roots(hg.degrees(), 6, seed=4)
     trees = smp.build_trees(roots)
-    got = trees.parent.cpu().numpy()
+    got = trees.parent_arrays().cpu().numpy()
     want = can.bfs_parents(hg.indptr, hg.adj, roots)
     assert np.array_equal(got, want)
     assert (got >= 0).sum() > 6 * 1000            # the roots' components are not trivial
@@ -115,13 +115,12 @@ def test_stream_replay_matches_reference(name, hub, cuda_device):
         assert got[k] == pf[pp[k]:pp[k + 1]].tolist()
 
 
-def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256, algo="walk", chunk_walks=32,
-                    depth1=True):
+def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, hub_threshold=256, depth1=True):
     import torch
     from graphgan_b200 import sampler as S
     from oracle import canonical as can
-    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold, algo, chunk_walks, depth1)
-    par = trees.parent.cpu().numpy()
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, roots, hub_threshold, depth1)
+    par = trees.parent_arrays().cpu().numpy()
     E = can.pad_rows(case.emb_g)
     bits = np.zeros(dg.n_bit_words, np.uint32)
     deg = hg.degrees()[roots]
@@ -154,12 +153,12 @@ def _philox_compare(case, cuda_device, roots, update_ratio, seed, n_sample_gen, 
     gp, rp = out_g.paths.cpu().numpy(), ref_g.paths
     for w in np.flatnonzero(ref_g.status == can.DONE):
         assert np.array_equal(gp[w, :ref_g.path_len[w]], rp[w, :ref_g.path_len[w]])
-    if algo == "walk":   # the start order of the walks (WalkPlan.start_order) must not change anything
-        assert smp.hub_first
-        smp.hub_first = False
-        out2 = smp.run(emb, bias, trees, sn, True, seed=seed, pass_tag=3, update_ratio=update_ratio)
-        for name in ("samples", "status", "wsteps", "wsuml", "root_ok", "first_edge"):
-            assert torch.equal(getattr(out2, name), getattr(out, name)), name
+    # the start order of the walks (WalkPlan.start_order) must not change anything
+    assert smp.hub_first
+    smp.hub_first = False
+    out2 = smp.run(emb, bias, trees, sn, True, seed=seed, pass_tag=3, update_ratio=update_ratio)
+    for name in ("samples", "status", "wsteps", "wsuml", "root_ok", "first_edge"):
+        assert torch.equal(getattr(out2, name), getattr(out, name)), name
     cg = out_g.counters_host()
     assert (cg["steps"], cg["sum_l"]) == (ref_g.steps, ref_g.sum_l)
     return cnt, cg
@@ -175,14 +174,13 @@ def test_philox_matches_canonical_oracle(name, ratio, hub, cuda_device):
                     hub_threshold=hub)
 
 
-@pytest.mark.parametrize("algo,depth1", [("walk", False), ("chunk", True)])
 @pytest.mark.parametrize("name,hub,ratio", [("rand300", 0, 0.6), ("rand1200", 256, 1.0), ("cagrqc", 8, 1.0)])
-def test_philox_other_kernels(name, hub, ratio, algo, depth1, cuda_device):
-    """The non-default order-free paths -- one warp per walk WITHOUT the depth-1 CDF reuse, and one warp per chunk
-    of walks (here with a ragged chunk size) -- agree bit for bit with the oracle (and so with the default path)."""
+def test_philox_without_depth1_reuse(name, hub, ratio, cuda_device):
+    """One warp per walk WITHOUT the depth-1 CDF reuse agrees bit for bit with the oracle (and so with the default
+    path)."""
     case = loader.load(name)
     _philox_compare(case, cuda_device, None, ratio, seed=4242, n_sample_gen=int(case.n_sample_gen), hub_threshold=hub,
-                    algo=algo, chunk_walks=5, depth1=depth1)
+                    depth1=False)
 
 
 @pytest.mark.parametrize("hub", [0, 64, 256])
@@ -200,8 +198,7 @@ def test_hub_lists_use_global_scratch(hub, cuda_device):
     case["graph"] = [hg.neighbors(i).tolist() for i in range(n)]
     rs = np.random.RandomState(0)
     roots = np.sort(rs.choice(np.flatnonzero(hg.degrees() > 0), 400, replace=False))
-    cnt, cg = _philox_compare(case, cuda_device, roots, 1.0, seed=99, n_sample_gen=6, hub_threshold=hub,
-                              algo={0: "walk", 64: "chunk", 256: "walk"}[hub], chunk_walks=8)
+    cnt, cg = _philox_compare(case, cuda_device, roots, 1.0, seed=99, n_sample_gen=6, hub_threshold=hub)
     assert cnt["steps"] > 0
     if hub:   # the reuse must actually remove row gathers
         assert cnt["rows_gathered"] < cnt["raw_sum_l"]
@@ -226,7 +223,7 @@ def test_giant_hub_lists_beyond_the_smem_score_buffer(hub, cuda_device):
     smp = S.WalkSampler(dg, hub_threshold=hub, depth1=True)
     roots = np.asarray([0, 3, 11, 200, 1999, 3599], np.int32)
     trees = smp.build_trees(roots)
-    par = trees.parent.cpu().numpy()
+    par = trees.parent_arrays().cpu().numpy()
     assert np.array_equal(par, can.bfs_parents(hg.indptr, hg.adj, roots))
     emb = S.pad_embedding(emb_h, cuda_device)
     bias_h = rs.normal(0, 0.2, n).astype(np.float32)
@@ -258,7 +255,7 @@ def test_partition_invariance(cuda_device):
     dg.reset_tree_mutations()
     parts = []
     for lo, hi in ((0, 500), (500, 1200)):
-        t = S.TreeBatch(trees.roots[lo:hi].contiguous(), trees.parent[lo:hi].contiguous())
+        t = trees.slice(lo, hi)
         o = smp.run(emb, bias, t, dg.raw_deg[lo:hi].contiguous(), True, seed=77, pass_tag=9)
         c, nb, lb, k = smp.emit_d_rows(o)
         k = int(k.item())
@@ -281,7 +278,7 @@ def test_wide_and_odd_embeddings(d, hub, cuda_device):
                        emb_g=synth.embeddings(n, d, seed=13, sigma=0.25), bias_g=np.random.RandomState(14).normal(0, 0.3, n).astype(np.float32))
     case["graph"] = [hg.neighbors(i).tolist() for i in range(n)]
     roots = np.sort(np.random.RandomState(1).choice(np.flatnonzero(hg.degrees() > 0), 300, replace=False))
-    _philox_compare(case, cuda_device, roots, 0.8, seed=321, n_sample_gen=7, hub_threshold=hub, algo="walk")
+    _philox_compare(case, cuda_device, roots, 0.8, seed=321, n_sample_gen=7, hub_threshold=hub)
 
 
 def test_empty_and_degenerate_batches(cuda_device):
@@ -290,16 +287,16 @@ def test_empty_and_degenerate_batches(cuda_device):
     import torch
     from graphgan_b200 import sampler as S
     case = loader.load("tiny")
-    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device, algo="walk")
+    hg, dg, smp, roots, trees, emb, bias = _setup(case, cuda_device)
     # (a) no roots at all
-    t0 = S.TreeBatch(trees.roots[:0].contiguous(), trees.parent[:0].contiguous())
+    t0 = trees.slice(0, 0)
     out = smp.run(emb, bias, t0, dg.raw_deg[:0].contiguous(), True, seed=1)
     assert out.n_walks == 0 and out.counters_host()["accepted"] == 0
     c, nb, lb, k = smp.emit_d_rows(out)
     assert int(k.item()) == 0
     # (b) only the isolated node 9 and the self-loop-only node 10 (graph_gan.py:252-253)
     sel = torch.as_tensor([9, 10]).to(cuda_device)
-    t1 = S.TreeBatch(trees.roots[sel].contiguous(), trees.parent[sel].contiguous())
+    t1 = trees.select(sel)
     out = smp.run(emb, bias, t1, dg.raw_deg[sel].contiguous(), True, seed=1)
     assert out.root_ok.cpu().tolist()[:2] == [0, 0] and out.counters_host()["accepted"] == 0
     out = smp.run(emb, bias, t1, 3, False, seed=1, max_path=8)       # G mode: paths_from_i is None
