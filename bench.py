@@ -43,8 +43,8 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="powerlaw_1m", choices=sorted(WORKLOADS))
     p.add_argument("--roots", type=int, default=16384,
-                   help="resident roots per GPU (R); the parent arrays take 4*N*R bytes (64 GB at N = 1M), capped at "
-                        "half of the device memory")
+                   help="resident roots per GPU (R); the tree rows take R * nnz / 8 bytes (41 GB at C3), capped at half of the "
+                        "device memory")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -52,6 +52,13 @@ def parse():
     p.add_argument("--file-order", action="store_true", help="start the walks in root order instead of hub-neighbourhoods first")
     p.add_argument("--no-depth1", dest="depth1", action="store_false",
                    help="disable the per-(root, depth-1 child) CDF reuse (csrc/walk.cu: step1_cdf_kernel)")
+    p.add_argument("--verify", type=int, default=12, help="roots of the last timed pass re-derived with the C oracle (0 = off)")
+    p.add_argument("--verify-seconds", type=float, default=45.0, help="time budget of --verify")
+    p.add_argument("--g-steps", type=int, default=5, help="timed generator-mode passes (0 = skip)")
+    p.add_argument("--pairs", type=int, default=1 << 22, help="--phase reward: pairs per launch")
+    p.add_argument("--bfs-roots", type=int, default=1184, help="--phase bfs: roots per launch (8 per SM)")
+    p.add_argument("--phase", default="sample", choices=["sample", "reward", "adam", "bfs", "update"],
+                   help="what to time: the D-sampling pass (the BASELINE metric) or one of the other kernels of the path")
     return p.parse_args()
 
 
@@ -73,10 +80,10 @@ def make_inputs(args, rank):
             pass
     emb = synth.embeddings(n, d, seed=args.seed + 1)
     n_roots = args.roots
-    if args.impl == "b200":      # "R chosen so parent[R, N] fits"
+    if args.impl == "b200":      # "R chosen so the trees fit"
         import torch
         total = torch.cuda.mem_get_info()[1]
-        n_roots = max(1, min(n_roots, int(total // 2 // (4 * n))))
+        n_roots = max(1, min(n_roots, int(total // 2 // (hg.adj.shape[0] // 8 + 8))))
         args.roots = n_roots
     # one seeded pool of R * world roots in ascending id order, dealt out round-robin: node ids follow the degree
     # ranking in the synthetic graphs, so every rank gets the same degree mix (the roots of a real pass would be
@@ -318,16 +325,92 @@ def workload_config(args, hg, d):
     return {"workload": "%s N=%d avg_deg=%d n_emb=%d, D-sampling pass over R=%d resident roots per GPU "
                         "(sample_num = deg(root), Philox RNG, update_ratio=1)" % (gen, n, deg, d, args.roots),
             "nnz": int(hg.adj.shape[0]), "max_deg": int(hg.max_deg),
-            "l2_policy": "inputs larger than L2 (embedding matrix %d MB, parent arrays %d MB)" % (
-                n * d * 4 >> 20, args.roots * n * 4 >> 20),
+            "l2_policy": "inputs larger than L2 (embedding matrix %d MB, tree rows %d MB)" % (
+                n * d * 4 >> 20, args.roots * (int(hg.adj.shape[0]) // 8) >> 20),
             "parallelism": "roots sharded over %d GPU(s), replicated graph+embeddings" % args.gpus}
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def _peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "hbm_gbs" in peaks:
+            return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, ValueError):
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_traffic(kernel, key):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture -- only when that capture was taken from the
+    library that is running now (content hash of csrc/ + include/); a stale capture reports null."""
+    try:
+        from graphgan_b200 import _build
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if t.get("source_hash") != _build.source_hash():
+            return None, "profiles/ncu_traffic.json was captured from other kernel sources (hash mismatch): not used"
+        v = t.get("kernels", {}).get(key, {}).get(kernel)
+        return (float(v), "profiles/ncu_traffic.json (%s)" % t.get("capture", "?")) if v is not None else (None, "no capture for %s" % key)
+    except (OSError, ValueError):
+        return None, "no ncu capture committed for these kernel sources"
+
+
+def _verify(args, hg, emb_h, roots, trees, out, smp, dev, seed, tag):
+    """Re-derive K roots of the LAST TIMED pass with the C oracle (oracle/gg_oracle.c: BFS tree + every walk of the root,
+    same Philox key) and compare the sampled nodes / statuses bit for bit."""
+    import torch
+    from oracle import canonical as can
+    K = min(args.verify, len(roots))
+    if K <= 0:
+        return None
+    deg = hg.degrees()[roots]
+    order = np.argsort(deg, kind="stable")
+    pick = np.unique(np.concatenate([np.linspace(0, len(roots) - 1, K - 1).astype(np.int64) if K > 1 else [],
+                                     [order[-1]]]).astype(np.int64))            # a spread of roots + the largest one
+    budget = float(args.verify_seconds)
+    t0 = time.time()
+    E = can.pad_rows(emb_h, smp_ld(emb_h))
+    bias0 = np.zeros(hg.n_node, np.float32)
+    wp = out.walk_ptr.cpu().numpy()
+    samples, status = out.samples.cpu().numpy(), out.status.cpu().numpy()
+    checked = walks = mism = tree_mism = 0
+    skipped = 0
+    for k in pick:
+        if time.time() - t0 > budget and checked > 0:
+            skipped += 1
+            continue
+        r = roots[k:k + 1]
+        par = can.bfs_parents(hg.indptr, hg.adj, r)
+        got_par = trees.parent_arrays(torch.as_tensor([int(k)], device=dev)).cpu().numpy()
+        tree_mism += int(not np.array_equal(par, got_par))
+        bits = np.zeros((hg.adj.shape[0] + 31) // 32 + 1, np.uint32)
+        ref = can.walk_pass(E, bias0, hg.indptr, hg.adj, r, par, deg[k:k + 1], True, bits, seed=seed, pass_tag=tag)
+        w0, w1 = int(wp[k]), int(wp[k + 1])
+        ok = bool(ref.root_ok[0])
+        if ok:
+            mism += int(np.count_nonzero(samples[w0:w1] != ref.samples)) + int(np.count_nonzero(status[w0:w1] != ref.status))
+        else:       # the reference voids the whole root: finalize blanks the walks after the first void
+            mism += int(out.root_ok[k].item() != 0)
+        checked += 1
+        walks += w1 - w0
+    return {"roots_checked": checked, "walks_checked": walks, "mismatches": mism, "tree_mismatches": tree_mism,
+            "roots_skipped_over_budget": skipped, "seconds": round(time.time() - t0, 2),
+            "oracle": "oracle/gg_oracle.c (T1): ggo_bfs_parent + ggo_walk_pass on the roots of the last timed pass"}
+
+
+def smp_ld(emb_h):
+    d = int(emb_h.shape[1])
+    ld = 32
+    while ld < d:
+        ld *= 2
+    return ld
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from graphgan_b200 import graph as G, sampler as S
+    from graphgan_b200.sampler import CNT
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -341,10 +424,16 @@ def run_b200(args):
     smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, depth1=args.depth1, hub_first=not args.file_order)
     emb = S.pad_embedding(emb_h, dev)
     bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
-    t0 = time.time()
-    trees = smp.build_trees(roots)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # ---- tree construction (outside the metric: "trees resident") -- timed on the device, reported
+    smp.build_trees(roots[:min(len(roots), 296)])                     # warm-up (allocates the builder's scratch)
     torch.cuda.synchronize()
-    t_bfs = time.time() - t0
+    e0, e1 = ev(), ev()
+    e0.record()
+    trees = smp.build_trees(roots)
+    e1.record()
+    torch.cuda.synchronize()
+    bfs_ms = e0.elapsed_time(e1)
     sample_num = dg.raw_deg[trees.roots.long()]
     W = int(sample_num.sum().item())
 
@@ -353,8 +442,17 @@ def run_b200(args):
     rows_pin = [torch.empty(2 * W, dtype=torch.int32).pin_memory() for _ in range(3)]
     nrows_pin = torch.zeros(1, dtype=torch.int64).pin_memory()
 
+    t0 = time.time()
     plan = smp.plan(trees, sample_num, True)
     reuse = smp.hub_threshold > 0
+    if reuse:
+        dg.hub_tiles(smp.hub_threshold)
+        if smp.depth1:
+            plan.depth1_buffers(smp)
+    if smp.hub_first:
+        plan.start_order(smp)
+    torch.cuda.synchronize()
+    plan_ms = 1e3 * (time.time() - t0)
 
     def step(tag, e2e=False, events=None):
         if e2e:
@@ -363,14 +461,21 @@ def run_b200(args):
             events[0].record()
         if reuse:                                                    # per-pass reuse: depends on the embeddings,
             smp.precompute(emb, bias, plan)                          # so it is part of every pass
-        if events is not None:
-            events[1].record()
-        out = smp.run(emb, bias, trees, sample_num, True, seed=args.seed, pass_tag=tag, finalize=False, plan=plan,
-                      precompute=False)
-        if events is not None:
+        if events is not None:                                       # (breakdown only: the two stages of gg_walk_sample
+            events[1].record()                                       # as two calls, so that each can be timed)
+            smp.run(emb, bias, trees, sample_num, True, seed=args.seed, pass_tag=tag, finalize=False, plan=plan,
+                    precompute=False, phase_mask=1)
             events[2].record()
+            out = smp.run(emb, bias, trees, sample_num, True, seed=args.seed, pass_tag=tag, finalize=False, plan=plan,
+                          precompute=False, phase_mask=2, zero_counters=False)
+            events[3].record()
+        else:
+            out = smp.run(emb, bias, trees, sample_num, True, seed=args.seed, pass_tag=tag, finalize=False, plan=plan,
+                          precompute=False)
         smp.finalize(out)
         c, nb, lb, n_rows = smp.emit_d_rows(out)
+        if events is not None:
+            events[4].record()
         if e2e:
             rows_pin[0].copy_(c, non_blocking=True); rows_pin[1].copy_(nb, non_blocking=True)
             rows_pin[2].copy_(lb, non_blocking=True); nrows_pin.copy_(n_rows, non_blocking=True)
@@ -385,67 +490,95 @@ def run_b200(args):
     def timed(e2e):
         for s in range(args.warmup):
             step(1000 + s, e2e)
-        evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
-        outs = []
         barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0, b1 = ev(), ev()
         t_start = time.time()
         b0.record()
-        cnts_live = []
+        cnts_live, out = [], None
         for s in range(args.steps):
-            out = step(2000 + s, e2e, evs[s])
+            out = step(2000 + s, e2e)
             cnts_live.append(out.counters.clone())                   # device-side copy, read after the region
         b1.record()
         barrier()
         t_end = time.time()
         ms = b0.elapsed_time(b1)
-        kern_ms = [(a.elapsed_time(b), b.elapsed_time(c)) for a, b, c in evs]
-        from graphgan_b200.sampler import CNT
         cnts = [{k: int(c[i]) for k, i in CNT.items()} for c in (x.cpu().numpy() for x in cnts_live)]
-        return ms, kern_ms, cnts, t_start, t_end
+        return ms, cnts, t_start, t_end, out
 
     clocks = ClockSampler(local)
     clocks.wait_first()
-    ms, kern_ms, cnts, t_start, t_end = timed(False)
+    ms, cnts, t_start, t_end, last_out = timed(False)
     clk = clocks.stop(t_start, t_end)
-    ms_e2e, _, cnts_e2e, _, _ = timed(True)
+    parity = None
+    if rank == 0 and args.verify > 0:
+        parity = _verify(args, hg, emb_h, roots, trees, last_out, smp, dev, args.seed, 2000 + args.steps - 1)
+    ms_e2e, cnts_e2e, _, _, _ = timed(True)
+
+    # ---- per-kernel breakdown (separate, untimed-for-the-headline passes; same work, stage boundaries evented)
+    nb_ = max(3, min(10, args.steps))
+    evs = [[ev() for _ in range(5)] for _ in range(nb_)]
+    bcnt = []
+    for s in range(nb_):
+        o = step(3000 + s, False, evs[s])
+        bcnt.append(o.counters.clone())
+    torch.cuda.synchronize()
+    stage = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evs]).mean(0)   # pre, depth1, walk, finalize+emit
+    brows = float(np.mean([int(c[CNT["rows_gathered"]]) for c in bcnt]))                       # walk_kernel only (phase 2)
+
+    # ---- generator-mode pass (prepare_data_for_g's walks: n_sample_gen per root, paths recorded)
+    g_stats = None
+    if args.g_steps > 0:
+        plan_g = smp.plan(trees, 20, False, 64)
+        def gstep(tag):
+            if reuse:
+                smp.precompute(emb, bias, plan_g)
+            return smp.run(emb, bias, trees, 20, False, seed=args.seed, pass_tag=tag, max_path=64, plan=plan_g, precompute=False)
+        for s in range(2):
+            gstep(4000 + s)
+        torch.cuda.synchronize()
+        g0, g1 = ev(), ev()
+        g0.record()
+        for s in range(args.g_steps):
+            og = gstep(4100 + s)
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / args.g_steps
+        gc = og.counters_host()
+        done = int((og.status == S.DONE).sum().item())
+        g_stats = {"samples_per_s": done / (gms * 1e-3), "ms_per_pass": gms, "walks": int(og.n_walks), "done": done,
+                   "steps_per_s": gc["steps"] / (gms * 1e-3), "path_overflow": gc["path_overflow"],
+                   "note": "G mode: 20 walks per root (config.n_sample_gen), paths recorded (max_path 64), trees as left by the D passes"}
 
     accepted = sum(c["accepted"] for c in cnts)
     accepted_e2e = sum(c["accepted"] for c in cnts_e2e)
-    tot = torch.tensor([float(accepted), float(accepted_e2e)], dtype=torch.float64, device=dev)
-    tmax = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(accepted), float(accepted_e2e), float(sum(c["steps"] for c in cnts)), float(W * args.steps)],
+                       dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms, ms_e2e, bfs_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tot, tmax = tot.cpu().numpy(), tmax.cpu().numpy()
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
-        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        # algorithmic bytes of one launch: per walk 4*ld (root row) + per candidate (4*ld + 8)
+        peak, peak_src = _peak()
         ld = int(emb.shape[1])
         c0 = cnts[-1]
-        alg_bytes = float(np.mean([W * 4 * ld + c["sum_l"] * (4 * ld + 8) for c in cnts]))
-        pre_ms, walk_ms = float(np.mean([k[0] for k in kern_ms])), float(np.mean([k[1] for k in kern_ms]))
-        k_ms = pre_ms + walk_ms
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        # rows the implementation really fetched: hub adjacency rows + small roots' neighbour rows (once per
-        # pass each) + what the walk kernel gathered on demand
+        row_b = 4 * ld + 8
+        pre_ms, d1_ms, walk_ms, fin_ms = (float(x) for x in stage)
+        k1_ms = pre_ms + d1_ms + walk_ms
+        # SURVEY 8d algorithmic bytes (every candidate row counted at every visit) -- an upper bound on the work a
+        # literal implementation would do, NOT what these kernels move (hub scores once per pass, one CDF per root,
+        # one per (root, child) pair): reported as the reuse ratio, never as a roofline fraction
+        survey_bytes = float(np.mean([W * 4 * ld + c["sum_l"] * row_b for c in cnts]))
         hub_edges = dg.hub_tiles(smp.hub_threshold)[3] if reuse else 0
         deg_w = np.diff(hg.indptr)[roots]
         root_rows = int(deg_w[deg_w < smp.hub_threshold].sum() + len(roots)) if reuse else 0
-        exec_rows = float(np.mean([c["rows_gathered"] for c in cnts])) + hub_edges + root_rows
-        exec_bytes = exec_rows * (4 * ld + 8)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "walk_traffic.json"))).get(
-                "%s@R%d" % (args.workload, args.roots))   # an ncu capture exists for the default configurations only
-        except (OSError, ValueError):
-            pass
+        all_rows = float(np.mean([c["rows_gathered"] for c in cnts])) + hub_edges + root_rows     # whole K1 stage
+        key = "%s@R%d" % (args.workload, args.roots)
+        traffic, traffic_src = _ncu_traffic("walk_kernel", key)
+        stage_traffic, _ = _ncu_traffic("k1_stage", key)
+        useful = brows * row_b                                       # embedding rows + bias + id the dominant kernel gathered
+        achieved = useful / (walk_ms * 1e-3) / 1e9
         line = {
             "metric": "sampled negative edges/sec (D-sampling pass)", "value": float(tot[0] / (tmax[0] * 1e-3)),
             "unit": "neg_edges/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -455,36 +588,225 @@ def run_b200(args):
             "e2e": {"value": float(tot[1] / (tmax[1] * 1e-3)), "unit": "neg_edges/s",
                     "h2d_bytes_per_step": int(roots_pin.numel() * 4),
                     "d2h_bytes_per_step": int(3 * 2 * W * 4 + 8),
-                    "call": "WalkSampler.run + finalize + emit_d_rows with pinned host roots in / rows out"},
+                    "call": "WalkSampler.precompute + run + finalize + emit_d_rows with pinned host roots in / rows out",
+                    "note": "trees and the walk plan of these roots are resident (SURVEY 8d); a NEW root batch also costs "
+                            "gg_bfs_build + the plan -- see full_pass"},
             "gpu_launches": ((9 if smp.depth1 else 7) if reuse else 5) * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "K1 stage: gg::hub_score_kernel + gg::root_cdf_kernel + gg_walk_sample (%sgg::walk_kernel) (ld=%d)" % (
-                             "gg::root_step_kernel + gg::step1_cdf_kernel + " if smp.depth1 else "", ld),
-                         "kernel_ms": k_ms, "precompute_ms": pre_ms, "walk_kernel_ms": walk_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "bytes_per_neg_edge": alg_bytes / max(c0["accepted"], 1),
-                         "executed_row_bytes_per_launch": exec_bytes,
-                         "executed_achieved": exec_bytes / (k_ms * 1e-3) / 1e9,
-                         "executed_frac": exec_bytes / (k_ms * 1e-3) / 1e9 / peak,
-                         "note": "achieved = SURVEY 8d algorithmic bytes (every candidate row counted at every visit) / "
-                                 "K1 stage time.  The implementation scores a hub's adjacency once per pass, builds one root "
-                                 "CDF per root and one step-1 CDF per (root, child) pair that several walks pick, and "
-                                 "re-read rows hit L2, so achieved exceeds the HBM copy peak by design; executed_* counts "
-                                 "the rows it really fetches (DESIGN.md 5); walk_kernel_ms is the whole gg_walk_sample call"},
+            "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": "gg::walk_kernel<%d> (dominant: %.0f %% of the K1 stage)" % (ld // 32, 100 * walk_ms / k1_ms),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel_ms": walk_ms,
+                         "useful_bytes_per_launch": useful, "useful_frac": achieved / peak,
+                         "dram_frac": (traffic / (walk_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "k1_stage": {"ms": k1_ms, "hub_scores_root_cdf_ms": pre_ms, "root_step_step1_cdf_ms": d1_ms,
+                                      "walk_kernel_ms": walk_ms, "finalize_emit_ms": fin_ms,
+                                      "useful_bytes": all_rows * row_b,
+                                      "useful_frac": all_rows * row_b / (k1_ms * 1e-3) / 1e9 / peak,
+                                      "dram_bytes": stage_traffic,
+                                      "dram_frac": (stage_traffic / (k1_ms * 1e-3) / 1e9 / peak) if stage_traffic else None},
+                         "survey_algorithmic_bytes_per_launch": survey_bytes,
+                         "algorithmic_reuse_ratio": survey_bytes / max(all_rows * row_b, 1.0),
+                         "bytes_per_neg_edge_survey": survey_bytes / max(c0["accepted"], 1),
+                         "note": "achieved = (embedding row + bias + id) bytes the walk kernel gathers on demand per launch / its "
+                                 "event-timed duration (frac = useful_frac); dram_frac uses ncu dram__bytes of the same kernel when "
+                                 "a capture of THESE sources is committed.  The kernel is latency-bound (dependent chain indptr -> "
+                                 "tree bits -> adj -> rows), not bandwidth-bound.  SURVEY 8d's formula counts every candidate row at "
+                                 "every visit; the kernels fetch algorithmic_reuse_ratio x fewer bytes (exact reuse, DESIGN.md 5)"},
+            "rates": {"walks_per_s": float(tot[3] / (tmax[0] * 1e-3)), "walk_steps_per_s": float(tot[2] / (tmax[0] * 1e-3)),
+                      "g_mode": g_stats},
+            "full_pass": {"neg_edges_per_s": c0["accepted"] / ((tmax[2] + plan_ms + tmax[0] / args.steps) * 1e-3),
+                          "bfs_build_ms": float(tmax[2]), "bfs_ms_per_root": float(tmax[2]) / len(roots), "plan_ms": plan_ms,
+                          "sampling_ms": float(tmax[0] / args.steps),
+                          "note": "one NEW root batch end to end: gg_bfs_build (device-timed) + walk plan (host wall clock, torch "
+                                  "plumbing) + one sampling pass; the headline metric keeps trees resident (SURVEY 8d)"},
             "walk": {"walks_per_step": W, "steps_per_neg_edge": c0["steps"] / max(c0["accepted"], 1),
                      "cands_per_neg_edge": c0["sum_l"] / max(c0["accepted"], 1), "ok_roots": c0["ok_roots"],
-                     "bfs_build_s": t_bfs,
                      "warp_cycle_share": {k[4:]: round(c0[k] / max(c0["cyc_walk"], 1), 4) for k in
                                           ("cyc_enum", "cyc_score", "cyc_choose", "cyc_step0", "cyc_step1", "cyc_step2p")}},
         }
         if not args.no_cpu_baseline and world >= 1:
-            def parent_rows(rs):   # reuse the GPU-built trees (checked against the oracle BFS in tests/)
+            def parent_rows(rs):   # reuse the GPU-built trees (checked against the oracle BFS in tests/ and in `parity`)
                 idx = np.searchsorted(roots, rs)
                 return trees.parent_arrays(torch.as_tensor(idx, device=dev)).cpu().numpy()
             ref = CpuReference(hg, emb_h, roots, args.cpu_seconds, 1, parent_rows=parent_rows)
             line["cpu_baseline"] = ref.run(args.seed)[0]
+            # the same roots on the GPU, so that the two numbers of this block describe identical inputs
+            idx = torch.as_tensor(np.searchsorted(roots, ref.sample), device=dev)
+            sub = trees.select(idx)
+            sn = dg.raw_deg[sub.roots.long()]
+            psub = smp.plan(sub, sn, True)
+            for s in range(3):
+                osub = smp.run(emb, bias, sub, sn, True, seed=args.seed, pass_tag=5000 + s, plan=psub)
+            torch.cuda.synchronize()
+            s0, s1 = ev(), ev()
+            s0.record()
+            for s in range(5):
+                osub = smp.run(emb, bias, sub, sn, True, seed=args.seed, pass_tag=5100 + s, plan=psub)
+            s1.record()
+            torch.cuda.synchronize()
+            line["cpu_baseline"]["gpu_same_roots"] = {
+                "value": osub.counters_host()["accepted"] / (s0.elapsed_time(s1) / 5 * 1e-3), "unit": "neg_edges/s",
+                "note": "this GPU on exactly the cpu_baseline's root sample (%d roots: too few walks to fill 148 SMs)" % len(ref.sample)}
             ref.close()
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ----------------------------------------------------------------------------- other kernels of the path
+def run_phase(args):
+    """One JSON line for a kernel of the path other than the D-sampling pass (not the BASELINE metric; these lines
+    exist so that every number quoted in DESIGN.md section 8 can be reproduced by a command):
+      --phase bfs     gg_bfs_build             trees/s        (graph_gan.py:84-108)
+      --phase reward  gg_pair_reward           pairs/s        (discriminator.py:33-34, called at graph_gan.py:220-222)
+      --phase adam    gg_adam_apply            steps/s        (TF1.8 dense Adam, generator.py:30-31)
+      --phase update  one data-parallel optimizer step: pair-grad slice -> NCCL all-gather -> merge -> Adam sweep"""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from graphgan_b200 import _cabi, graph as G, sampler as S
+    from graphgan_b200._cabi import ptr
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gen, n, deg, d = WORKLOADS[args.workload]
+    peak, peak_src = _peak()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    lib = _cabi.lib()
+    st = lambda: torch.cuda.current_stream(dev).cuda_stream
+    ld = smp_ld(np.empty((1, d)))
+    clocks = ClockSampler(local)
+    clocks.wait_first()
+
+    def time_steps(fn, flush=None):
+        for s in range(args.warmup):
+            fn(s)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        tot = 0.0
+        for s in range(args.steps):
+            if flush is not None:
+                flush()
+            a, b = ev(), ev()
+            a.record(); fn(args.warmup + s); b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), t0, time.time()
+
+    line = {"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "phase": args.phase}
+    if args.phase == "bfs":
+        hg, emb_h, roots, d = make_inputs(args, rank)
+        dg = G.DeviceGraph(hg, dev)
+        smp = S.WalkSampler(dg)
+        R = min(len(roots), args.bfs_roots)
+        rr = roots[np.linspace(0, len(roots) - 1, R).astype(np.int64)]
+        holder = {}
+        def fn(s):
+            holder["t"] = smp.build_trees(rr)
+        ms, t0, t1 = time_steps(fn)
+        nnz = int(hg.adj.shape[0])
+        alg = R * (4.0 * nnz + nnz / 8.0 + 8.0 * n)          # adjacency once + tree row + queue write/read, per root
+        k_ms = ms / args.steps
+        line.update({"metric": "BFS trees built/sec (gg_bfs_build)", "value": R * world * args.steps / (ms * 1e-3), "unit": "trees/s",
+                     "ms_per_step": k_ms, "scaling": "weak",
+                     "config": {"workload": "%s N=%d avg_deg=%d: gg_bfs_build of %d roots per GPU" % (gen, n, deg, R), "nnz": nnz,
+                                "l2_policy": "tree rows (%d MB per step) exceed L2; the adjacency (%d MB) is shared by all roots and stays in L2"
+                                             % (R * (nnz // 8) >> 20, nnz * 4 >> 20)},
+                     "ms_per_root": k_ms / R, "gpu_launches": args.steps,
+                     "roofline": {"bound": "hbm", "kernel": "gg::bfs_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak,
+                                  "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                  "algorithmic_bytes_per_launch": alg,
+                                  "note": "bytes = per root: adjacency 4*nnz (read once, served by L2: one copy for all roots) + tree row "
+                                          "nnz/8 + queue 8*N; the builder is bound by shared-memory atomics / barriers, not by HBM"}})
+    elif args.phase in ("reward", "adam", "update"):
+        g = torch.Generator(device=dev); g.manual_seed(args.seed + 5)
+        emb = torch.empty((n, ld), dtype=torch.float32, device=dev).normal_(0, 0.5, generator=g)
+        if ld > d:
+            emb[:, d:] = 0
+        bias = torch.zeros(n, dtype=torch.float32, device=dev)
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush = lambda: flush_buf.zero_()
+        if args.phase == "reward":
+            M = args.pairs
+            i = torch.randint(0, n, (M,), device=dev, dtype=torch.int32, generator=g)
+            j = torch.randint(0, n, (M,), device=dev, dtype=torch.int32, generator=g)
+            out = torch.empty(M, dtype=torch.float32, device=dev)
+            def fn(s):
+                _cabi.check(lib.gg_pair_reward(M, ptr(i), ptr(j), ptr(emb), ptr(bias), ld, ptr(out), st()), "gg_pair_reward")
+            ms, t0, t1 = time_steps(fn, flush)
+            k_ms = ms / args.steps
+            alg = M * (8.0 * ld + 12)
+            line.update({"metric": "discriminator.reward pairs/sec (gg_pair_reward)", "value": M * world * args.steps / (ms * 1e-3),
+                         "unit": "pairs/s", "ms_per_step": k_ms, "scaling": "weak", "gpu_launches": args.steps,
+                         "config": {"workload": "N=%d n_emb=%d, %d uniform random pairs per launch" % (n, d, M),
+                                    "l2_policy": "L2 flushed between launches (256 MB memset); embedding matrix %d MB" % (n * ld * 4 >> 20)},
+                         "roofline": {"bound": "hbm", "kernel": "gg::reward_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak,
+                                      "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                      "algorithmic_bytes_per_launch": alg, "note": "8*ld + 12 bytes per pair (two rows, two ids, one bias-free score out)"}})
+        else:
+            from graphgan_b200.discriminator import Discriminator
+            from graphgan_b200 import config as cfg
+            cfg.device = str(dev)
+            m = Discriminator(n, emb[:, :d], device=dev)
+            B = 64
+            i = torch.randint(0, n, (B,), device=dev, dtype=torch.int32, generator=g)
+            j = torch.randint(0, n, (B,), device=dev, dtype=torch.int32, generator=g)
+            lab = (torch.rand(B, device=dev, generator=g) < 0.5).float()
+            alg = 24.0 * n * ld
+            if args.phase == "adam":
+                m.step(i, j, lab)
+                def fn(s):
+                    m.apply_adam()
+                ms, t0, t1 = time_steps(fn)
+                k_ms = ms / args.steps
+                line.update({"metric": "TF1.8 dense Adam sweeps/sec (gg_adam_apply)", "value": world * args.steps / (ms * 1e-3), "unit": "steps/s",
+                             "ms_per_step": k_ms, "scaling": "weak", "gpu_launches": args.steps,
+                             "config": {"workload": "N=%d n_emb=%d (ld %d): one dense Adam sweep over E, m, v per step" % (n, d, ld),
+                                        "l2_policy": "inputs larger than L2 (E, m, v = %d MB)" % (3 * n * ld * 4 >> 20)},
+                             "roofline": {"bound": "hbm", "kernel": "gg::adam_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak,
+                                          "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                          "algorithmic_bytes_per_launch": alg, "note": "24 * N * ld bytes per step: read + write of E, m, v"}})
+            else:
+                from graphgan_b200.parallel import DataParallelStep
+                dp = DataParallelStep(m) if world > 1 else None
+                def fn(s):
+                    if dp is not None:
+                        dp.step(i, j, lab)
+                    else:
+                        m.step(i, j, lab)
+                ms, t0, t1 = time_steps(fn)
+                k_ms = ms / args.steps
+                extra = dp.stats() if dp is not None else {}
+                line.update({"metric": "optimizer steps/sec (64-pair discriminator step, data parallel)", "value": args.steps / (ms * 1e-3),
+                             "unit": "steps/s", "ms_per_step": k_ms, "scaling": "strong",
+                             "gpu_launches": (4 if world > 1 else 2) * args.steps,
+                             "config": {"workload": "N=%d n_emb=%d (ld %d): one 64-pair d_updates step = pair-grad on this rank's slice -> "
+                                                    "%s -> merge -> dense Adam sweep" % (n, d, ld, "ncclAllGather of the compact gradients (C ABI: gg_dp_step)" if world > 1 else "no collective (1 GPU)"),
+                                        "l2_policy": "inputs larger than L2 (E, m, v = %d MB)" % (3 * n * ld * 4 >> 20),
+                                        "parallelism": "replicated parameters, batch rows split over %d GPU(s)" % world},
+                             "collective": extra,
+                             "roofline": {"bound": "hbm", "kernel": "gg::adam_kernel (the sweep dominates the step)", "achieved": alg / (k_ms * 1e-3) / 1e9,
+                                          "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                                          "note": "whole step time against the sweep's 24 * N * ld bytes: the collective and the 64-pair gradient are the difference to --phase adam"}})
+    line["clocks"] = clocks.stop(t0, t1)
+    line["e2e"] = {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "device-resident kernel line (not the BASELINE metric); the plugin-level e2e number is the default --phase sample"}
+    if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -515,6 +837,8 @@ def main():
         _RESULT_FD = None
     if args.impl == "reference":
         return run_reference(args)
+    if args.phase != "sample":
+        return run_phase(args)
     return run_b200(args)
 
 

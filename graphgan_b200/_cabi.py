@@ -26,7 +26,7 @@ class WalkDesc(C.Structure):
         ("n_walks", C.c_int64), ("for_d", C.c_int32), ("rng_mode", C.c_int32), ("d1_bits", C.c_void_p),
         ("seed", C.c_uint64), ("pass_tag", C.c_uint32), ("max_path", C.c_int32),
         ("stream", C.c_void_p), ("n_stream", C.c_int64), ("update_ratio", C.c_double),
-        ("max_cand", C.c_int32), ("reserved", C.c_int32),
+        ("max_cand", C.c_int32), ("phase_mask", C.c_int32),
         ("samples", C.c_void_p), ("status", C.c_void_p), ("first_edge", C.c_void_p), ("wsteps", C.c_void_p),
         ("wsuml", C.c_void_p), ("paths", C.c_void_p), ("path_len", C.c_void_p), ("counters", C.c_void_p),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64), ("work_counter", C.c_void_p),
@@ -57,6 +57,14 @@ SIGNATURES = {
     "gg_pair_grad": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _F, _P, _P, _P, _P, _P, _P]),
     "gg_grad_buf_floats": (_I64, [_I32, _I32]),
     "gg_grad_merge": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "gg_comm_unique_id": (C.c_int, [_P]),
+    "gg_comm_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
+    "gg_comm_destroy": (C.c_int, [_P]),
+    "gg_comm_info": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32), C.POINTER(C.c_uint64)]),
+    "gg_dp_step": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I32, _P, _P, _P, _P, _P,
+                            _F, _F, _F, _F, _P]),
+    "gg_dp_train_steps": (C.c_int, [_P, _I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I32,
+                                   _P, _P, _P, _P, _P, _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
     "gg_adam_apply": (C.c_int, [_I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),
     "gg_train_steps": (C.c_int, [_I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P,
                                 _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),

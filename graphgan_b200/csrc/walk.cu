@@ -536,7 +536,8 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
     } else {
         const int ctas = gg::grid_ctas();
         GG_REQUIRE(d.scratch_bytes >= (int64_t)ctas * gg::WARPS_PER_CTA * 2 * d.max_cand * 4, "scratch too small");
-        if (d.s1_q) {   // depth-1 reuse: root steps + one CDF per (root, child) pair that occurs
+        const int pm = d.phase_mask ? d.phase_mask : 3;   // 1 = depth-1 precompute, 2 = walk kernel (default both)
+        if (d.s1_q && (pm & 1)) {   // depth-1 reuse: root steps + one CDF per (root, child) pair that occurs
             GG_REQUIRE(d.root_q && d.walk_slot && d.first_idx && d.s1_cnt && d.s1_n && d.s1_ptr && d.s1_ids && d.s1_slot,
                        "depth-1 reuse needs root_q, walk_slot and the s1_* buffers");
             GG_CHECK(cudaMemsetAsync(d.s1_cnt, 0, sizeof(int32_t) * (size_t)d.s1_nq, st));
@@ -557,6 +558,7 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
             GG_CHECK(cudaGetLastError());
             GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));   // the walk kernel's queue starts at 0
         }
+        if (!(pm & 2)) return 0;
         switch (cpl) {
 #define GG_WALK(C)                                                                                                    \
     GG_CHECK(cudaFuncSetAttribute(gg::walk_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \

@@ -244,9 +244,7 @@ class GraphGAN(object):
                 self.shuffle_rng.shuffle(start_list)
                 # the per-batch sess.run loop of graph_gan.py:152-157, enqueued from C (identical steps)
                 if self.dist:
-                    for start in start_list:
-                        end = start + config.batch_size_dis
-                        self._dp_d.step(center_nodes[start:end], neighbor_nodes[start:end], labels[start:end])
+                    self._dp_d.train_steps(center_nodes, neighbor_nodes, labels, start_list, config.batch_size_dis)
                 else:
                     self.discriminator.train_steps(center_nodes, neighbor_nodes, labels, start_list, config.batch_size_dis)
             # G-steps
@@ -258,9 +256,7 @@ class GraphGAN(object):
                 start_list = list(range(0, train_size, config.batch_size_gen))
                 self.shuffle_rng.shuffle(start_list)
                 if self.dist:
-                    for start in start_list:
-                        end = start + config.batch_size_gen
-                        self._dp_g.step(node_1[start:end], node_2[start:end], reward[start:end])
+                    self._dp_g.train_steps(node_1, node_2, reward, start_list, config.batch_size_gen)
                 else:
                     self.generator.train_steps(node_1, node_2, reward, start_list, config.batch_size_gen)   # graph_gan.py:171-176
             self.write_embeddings_to_file()

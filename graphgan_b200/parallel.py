@@ -8,7 +8,8 @@ all-gathered so that every rank sees the same training set (the reference's list
 Updates are data parallel: every rank scores its slice of the 64-pair batch (K2), ONE collective per step
 exchanges the compact gradients (ids + summed rows; a few KB, latency bound, NVLS-friendly), every rank merges
 them in the same rank-major order (gg_grad_merge) and applies the same K3 Adam sweep, so replicas stay
-bit-identical without broadcasting parameters.
+bit-identical without broadcasting parameters.  The step lives in the C library (csrc/comm.cu: gg_dp_step,
+gg_dp_train_steps) with a library-owned NCCL communicator; torch.distributed only carries the 128-byte unique id.
 """
 import ctypes as C
 
@@ -53,9 +54,31 @@ def all_gather_varlen(t, group=None):
     return torch.cat([o[:k] for o, k in zip(outs, sizes)])
 
 
+def create_comm(group=None):
+    """NCCL communicator OWNED BY THE C LIBRARY (csrc/comm.cu) over the ranks of `group`: rank 0 creates the unique id,
+    torch.distributed (any backend) broadcasts its 128 bytes, every rank calls ncclCommInitRank on its current device."""
+    import torch
+    import torch.distributed as dist
+    lib = _cabi.lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _cabi.check(lib.gg_comm_unique_id(buf), "gg_comm_unique_id")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = bytes(t.cpu().numpy().tobytes())
+    handle = C.c_void_p()
+    _cabi.check(lib.gg_comm_init(C.create_string_buffer(raw, 128), rank, world, C.byref(handle)), "gg_comm_init")
+    return handle
+
+
 class DataParallelStep:
-    """Data-parallel replacement for PairModel.step: same arguments (the WHOLE mini-batch, identical on
-    every rank), one collective per step."""
+    """Data-parallel replacement for PairModel.step / train_steps: same arguments (the WHOLE mini-batch, identical on
+    every rank).  The step -- gradient of this rank's rows, ONE ncclAllGather of the compact gradients, rank-major merge,
+    Adam sweep -- runs inside the C library on the caller's stream (gg_dp_step / gg_dp_train_steps)."""
+
+    _comm = None        # one library-owned communicator per process
 
     def __init__(self, model, group=None):
         import torch
@@ -63,6 +86,9 @@ class DataParallelStep:
         self.torch, self.dist, self.model, self.group = torch, dist, model, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.lib = _cabi.lib()
+        if DataParallelStep._comm is None:
+            DataParallelStep._comm = create_comm(group)
+        self.comm = DataParallelStep._comm
         self._cap = None
 
     def _buffers(self, cap):
@@ -71,7 +97,6 @@ class DataParallelStep:
             nf = int(self.lib.gg_grad_buf_floats(cap, m.ld))
             self.local = torch.zeros(nf, dtype=torch.float32, device=m.device)
             self.gathered = torch.empty(self.world * nf, dtype=torch.float32, device=m.device)
-            self.slot_tmp = None
             self._cap, self._nf = cap, nf
         return self.local, self.gathered
 
@@ -81,19 +106,40 @@ class DataParallelStep:
         B = int(i.shape[0])
         if B == 0:
             return
-        lo, hi = block_range(B, self.rank, self.world)
         cap = 2 * (-(-B // self.world))
         local, gathered = self._buffers(cap)
-        ld, st = m.ld, m._stream()
-        base = local.data_ptr()
-        rows_p, bias_p, ids_p, nu_p = base, base + 4 * cap * ld, base + 4 * (cap * ld + cap), base + 4 * (cap * ld + 2 * cap)
-        if hi > lo:
-            _cabi.check(self.lib.gg_pair_grad(m._step_mode, hi - lo, B, ptr(i[lo:hi]), ptr(j[lo:hi]), ptr(a[lo:hi]), ptr(m.emb),
-                                              ptr(m.bias_t), ld, C.c_float(float(m.lam)), nu_p, ids_p, rows_p, bias_p,
-                                              ptr(m.row_slot), st), "gg_pair_grad")
-        else:
-            local[cap * ld + 2 * cap:].zero_()     # n_unique = 0
-        self.dist.all_gather_into_tensor(gathered, local, group=self.group)   # the step's only collective
-        _cabi.check(self.lib.gg_grad_merge(self.world, cap, ld, ptr(gathered), ptr(m.n_unique), ptr(m.uniq_ids),
-                                           ptr(m.grad_rows), ptr(m.grad_bias), ptr(m.row_slot), st), "gg_grad_merge")
-        m.apply_adam()
+        f = lambda x: C.c_float(float(x))
+        _cabi.check(self.lib.gg_dp_step(self.comm, m._step_mode, B, ptr(i), ptr(j), ptr(a), m.n_node, m.ld, ptr(m.emb), ptr(m.m_emb),
+                                        ptr(m.v_emb), ptr(m.bias_t), ptr(m.m_bias), ptr(m.v_bias), f(m.lam), ptr(local), ptr(gathered),
+                                        cap, ptr(m.n_unique), ptr(m.uniq_ids), ptr(m.grad_rows), ptr(m.grad_bias), ptr(m.row_slot),
+                                        f(m.lr_t()), f(m.beta1), f(m.beta2), f(m.eps), m._stream()), "gg_dp_step")
+        m.beta1_power = np.float32(m.beta1_power * m.beta1)
+        m.beta2_power = np.float32(m.beta2_power * m.beta2)
+        m.step_count += 1
+
+    def train_steps(self, node_id, node_neighbor_id, aux, start_list, batch_size):
+        """All steps of one inner epoch (graph_gan.py:149-157 / 168-176) enqueued from C, one collective each."""
+        m = self.model
+        i, j, a = m._dev_i32(node_id), m._dev_i32(node_neighbor_id), m._dev_f32(aux)
+        starts = np.ascontiguousarray(np.asarray(start_list, np.int64))
+        if starts.size == 0:
+            return
+        cap = 2 * (-(-int(batch_size) // self.world))
+        local, gathered = self._buffers(cap)
+        f = lambda x: C.c_float(float(x))
+        b1p, b2p = f(m.beta1_power), f(m.beta2_power)
+        _cabi.check(self.lib.gg_dp_train_steps(self.comm, m._step_mode, int(i.shape[0]), starts.ctypes.data_as(C.c_void_p),
+                                               int(starts.size), int(batch_size), ptr(i), ptr(j), ptr(a), m.n_node, m.ld,
+                                               ptr(m.emb), ptr(m.m_emb), ptr(m.v_emb), ptr(m.bias_t), ptr(m.m_bias), ptr(m.v_bias),
+                                               f(m.lam), ptr(local), ptr(gathered), cap, ptr(m.n_unique), ptr(m.uniq_ids),
+                                               ptr(m.grad_rows), ptr(m.grad_bias), ptr(m.row_slot), f(m.lr), f(m.beta1), f(m.beta2),
+                                               f(m.eps), C.byref(b1p), C.byref(b2p), m._stream()), "gg_dp_train_steps")
+        self._keep = (i, j, a)
+        m.beta1_power, m.beta2_power = np.float32(b1p.value), np.float32(b2p.value)
+        m.step_count += int(starts.size)
+
+    def stats(self):
+        r, w, v, n = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_uint64(0)
+        _cabi.check(self.lib.gg_comm_info(self.comm, C.byref(r), C.byref(w), C.byref(v), C.byref(n)), "gg_comm_info")
+        return {"rank": r.value, "comm_nranks": w.value, "nccl_version": v.value, "collectives_issued": int(n.value),
+                "bytes_per_rank_per_step": 4 * int(getattr(self, "_nf", 0)), "kind": "ncclAllGather (fp32) inside gg_dp_step"}

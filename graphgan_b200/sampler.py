@@ -207,7 +207,7 @@ class WalkSampler:
     def plan(self, trees, sample_num, for_d, max_path=0):
         return WalkPlan(self, trees, sample_num, for_d, max_path)
 
-    def _desc(self, emb, bias, plan, *, seed, pass_tag, update_ratio, rng_mode, stream, reuse):
+    def _desc(self, emb, bias, plan, *, seed, pass_tag, update_ratio, rng_mode, stream, reuse, phase_mask=0):
         torch = self.torch
         assert emb.dtype == torch.float32 and emb.is_contiguous() and bias.dtype == torch.float32
         t, d = plan.trees, _cabi.WalkDesc()
@@ -218,7 +218,7 @@ class WalkSampler:
         d.for_d, d.rng_mode, d.d1_bits = int(plan.for_d), rng_mode, ptr(self.g.d1_bits)
         d.seed, d.pass_tag, d.max_path = seed, pass_tag, plan.max_path
         d.stream, d.n_stream = (ptr(stream), int(stream.numel())) if stream is not None else (None, 0)
-        d.update_ratio, d.max_cand = float(update_ratio), self.max_cand
+        d.update_ratio, d.max_cand, d.phase_mask = float(update_ratio), self.max_cand, int(phase_mask)
         d.samples, d.status, d.first_edge, d.wsteps, d.wsuml = (ptr(plan.samples), ptr(plan.status), ptr(plan.first_edge),
                                                                  ptr(plan.wsteps), ptr(plan.wsuml))
         d.paths, d.path_len, d.counters = ptr(plan.paths), ptr(plan.path_len), ptr(plan.counters)
@@ -249,16 +249,17 @@ class WalkSampler:
         _cabi.check(self.lib.gg_root_cdf(C.byref(d), ptr(plan.root_sc), ptr(plan.root_q), st), "gg_root_cdf")
 
     def run(self, emb, bias, trees, sample_num, for_d, *, seed=0, pass_tag=0, update_ratio=1.0, max_path=0,
-            rng_mode=RNG_PHILOX, stream=None, finalize=True, plan=None, reuse=None, precompute=True):
+            rng_mode=RNG_PHILOX, stream=None, finalize=True, plan=None, reuse=None, precompute=True, phase_mask=0, zero_counters=True):
         """All walks of one pass.  ``sample_num``: int (G mode, config.n_sample_gen) or device int64 [R]
         (D mode, len(graph[root])).  ``reuse`` (default: hub_threshold > 0) turns the per-pass score / CDF
         reuse on; results are bit-identical either way."""
         if plan is None:
             plan = self.plan(trees, sample_num, for_d, max_path)
         reuse = (self.hub_threshold > 0) if reuse is None else bool(reuse)
-        plan.counters.zero_()
+        if zero_counters:
+            plan.counters.zero_()
         d = self._desc(emb, bias, plan, seed=seed, pass_tag=pass_tag, update_ratio=update_ratio, rng_mode=rng_mode,
-                       stream=stream, reuse=reuse)
+                       stream=stream, reuse=reuse, phase_mask=phase_mask)
         if reuse and precompute:
             self.precompute(emb, bias, plan, d)
         _cabi.check(self.lib.gg_walk_sample(C.byref(d), self._stream()), "gg_walk_sample")

@@ -84,7 +84,8 @@ typedef struct gg_walk_desc {
     int64_t n_stream;
     double update_ratio;        /* config.update_ratio (graph_gan.py:189/209) */
     int32_t max_cand;           /* >= max walk-CSR degree + 1 */
-    int32_t reserved;
+    int32_t phase_mask;         /* 0 = whole call; 1 = only the depth-1 precompute (root steps + per-pair CDFs), 2 = only
+                                   the walk kernel -- lets a profiler time the two stages of one pass separately */
     /* per-walk outputs, device [W] */
     int32_t *samples;           /* sampled node (graph_gan.py:265) or -1 */
     int32_t *status;
@@ -206,6 +207,37 @@ int gg_pair_grad(int32_t mode, int32_t n_pairs, int32_t batch_total, const int32
 int64_t gg_grad_buf_floats(int32_t cap, int32_t ld);
 int gg_grad_merge(int32_t world, int32_t cap, int32_t ld, const float *gathered, int32_t *n_unique,
                   int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel optimizer step with its collective inside the library (csrc/comm.cu).  N replicas of the
+ * per-batch loops of graph_gan.py:149-157 / 168-176: every rank computes the gradient of ITS rows of the mini-batch
+ * (gg_pair_grad with batch_total), ONE ncclAllGather exchanges the compact gradients over NVLink, every rank merges
+ * them in rank-major order (gg_grad_merge) and applies the same Adam sweep -- replicas stay bit-identical.
+ *   gg_comm_unique_id : ncclGetUniqueId (128 bytes; rank 0 creates it, the caller broadcasts it out of band)
+ *   gg_comm_init      : ncclCommInitRank on the CURRENT device -> opaque handle
+ *   gg_dp_step        : the whole step on `stream` (node_id / node_neighbor_id / aux: the WHOLE batch, device, identical
+ *                       on all ranks; local_buf: gg_grad_buf_floats(cap, ld) floats; gathered_buf: world times that;
+ *                       cap >= 2 * ceil(n_pairs / world))
+ *   gg_dp_train_steps : gg_dp_step for every start of a (host) shuffled start list, enqueued from C; beta powers as in
+ *                       gg_train_steps
+ * NCCL is dlopen-ed at first use (the process's already-loaded libnccl.so.2 if there is one).
+ * ------------------------------------------------------------------------------------------ */
+int gg_comm_unique_id(void *id128);
+int gg_comm_init(const void *id128, int32_t rank, int32_t world, void **comm_out);
+int gg_comm_destroy(void *comm);
+int gg_comm_info(void *comm, int32_t *rank, int32_t *world, int32_t *nccl_version, uint64_t *collectives);
+int gg_dp_step(void *comm, int32_t mode, int32_t n_pairs, const int32_t *node_id, const int32_t *node_neighbor_id,
+               const float *aux, int64_t n_node, int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias,
+               float *m_bias, float *v_bias, float lambda, float *local_buf, float *gathered_buf, int32_t cap,
+               int32_t *n_unique, int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot,
+               float lr_t, float beta1, float beta2, float eps, void *stream);
+int gg_dp_train_steps(void *comm, int32_t mode, int64_t n_rows, const int64_t *start_list, int64_t n_starts,
+                      int32_t batch_size, const int32_t *node_id, const int32_t *node_neighbor_id, const float *aux,
+                      int64_t n_node, int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias,
+                      float *v_bias, float lambda, float *local_buf, float *gathered_buf, int32_t cap,
+                      int32_t *n_unique, int32_t *uniq_ids, float *grad_rows, float *grad_bias, int32_t *row_slot,
+                      float lr, float beta1, float beta2, float eps, float *beta1_power, float *beta2_power,
+                      void *stream);
 
 /* K3: TF1.8 AdamOptimizer sparse apply == dense decay (generator.py:30-31,
  * discriminator.py:31-32): m <- b1*m (+ (1-b1) g on touched rows), v likewise, then for ALL
