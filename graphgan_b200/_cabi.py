@@ -72,6 +72,9 @@ SIGNATURES = {
                                _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
     "gg_train_fused": (C.c_int, [_I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _F,
                                 _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
+    "gg_pair_dot_f64": (C.c_int, [_I64, _P, _P, _P, _I32, _P, _P]),
+    "gg_link_pred_acc": (C.c_int, [_I64, _P, _P, _P]),
+    "gg_unpad_rows": (C.c_int, [_I64, _I32, _I32, _P, _P, _P]),
     "gg_window_pairs": (C.c_int, [_I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _I64, _P]),
 }
 

@@ -53,5 +53,6 @@ seed = 0                            # Philox key of the walk sampler and seed of
 root_batch = 4096                   # roots whose BFS tree rows are resident at once (nnz / 8 bytes each)
 tree_cache_bytes = 8 << 30          # keep ALL trees resident (like the reference's cache) below this size
 max_path_len = 64                   # row stride of recorded generator paths; a longer walk is an error
-binary_embeddings = False           # also dump <emb_filename>.f32 ([N, n_emb] fp32, row-major) every epoch
+text_embeddings = True              # the reference's text dump (graph_gan.py:293-306); turn off at N >= 1e5 (minutes per epoch)
+binary_embeddings = False           # also dump <emb_filename>.f32 (header + [N, n_emb] fp32, row-major) every epoch
 device_eval = True                  # link-prediction check on the GPU (io/evaluation text round trip skipped)

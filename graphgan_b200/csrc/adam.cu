@@ -34,7 +34,7 @@ extern "C" int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_em
                              float beta2, float eps, void *stream) {
     (void)n_unique; (void)uniq_ids;
     GG_REQUIRE(emb && m_emb && v_emb && bias && m_bias && v_bias && grad_rows && grad_bias && row_slot, "null pointer");
-    GG_REQUIRE(ld > 0 && ld % 32 == 0, "ld must be a positive multiple of 32");
+    GG_REQUIRE(ld == 32 || ld == 64 || ld == 128 || ld == 256, "ld must be 32, 64, 128 or 256 (row stride in floats)");
     if (n_node == 0) return 0;
     const int q = ld / 4;                                                       // float4 per row
     const long long nseg = q >= 32 ? n_node * (q / 32) : (n_node + 32 / q - 1) / (32 / q);   // 512-byte segments

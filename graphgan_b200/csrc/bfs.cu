@@ -24,7 +24,7 @@
 //   * winners are compacted in entry order (a block scan) = FIFO order, appended to the queue, and their bits are
 //     OR-ed into the root's tree row.
 //
-// The only global traffic is the adjacency stream (shared by all roots, L2), the queue (4 N bytes per root, written
+// The only global traffic is the adjacency stream (shared by all roots, L2), the queue (8 N bytes per root, written
 // and read once, sequentially) and the tree row itself.  No per-root claim / parent / offset arrays (the round-1
 // builder kept 32 N bytes of them per concurrent root and was bound by random DRAM sectors).
 // HBM/L2-bound integer work; no tensor cores.
@@ -39,12 +39,13 @@ constexpr unsigned BFS_SLAB = BFS_THREADS * BFS_EPT;       // 8192 entries
 constexpr int BFS_HBITS = 14;
 constexpr unsigned BFS_HSLOTS = 1u << BFS_HBITS;           // 16384 slots, 64 KB
 constexpr unsigned BFS_EMPTY = 0xffffffffu;
-// shared memory: table | start[1025] | a0[1024] | warp totals[32] | pad | bitmap
-constexpr unsigned BFS_FIXED_WORDS = BFS_HSLOTS + (BFS_THREADS + 1) + BFS_THREADS + 32 + 31;
+// shared memory: table | start[1025] | a0[1024] | warp totals[2][32] | pad | bitmap
+constexpr unsigned BFS_FIXED_WORDS = BFS_HSLOTS + (BFS_THREADS + 1) + BFS_THREADS + 64 + 31;
 constexpr long long BFS_SMEM_MAX_BYTES = 227 * 1024;
 constexpr long long BFS_SMEM_BITMAP_MAX_BYTES = BFS_SMEM_MAX_BYTES - 4ll * BFS_FIXED_WORDS;
 
-// inclusive block scan (1024 threads); `total` = sum over the block.  Ends with a barrier, so s_tot may be reused.
+// inclusive block scan (1024 threads); `total` = sum over the block.  Two barriers; consecutive calls must alternate
+// between the two halves of s_tot (a fast warp's next scan may not overwrite totals a slow warp still reads).
 __device__ __forceinline__ unsigned block_scan_incl(unsigned v, unsigned *s_tot, unsigned &total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned x = v;
@@ -55,20 +56,15 @@ __device__ __forceinline__ unsigned block_scan_incl(unsigned v, unsigned *s_tot,
     }
     if (lane == 31) s_tot[wid] = x;
     __syncthreads();
-    if (wid == 0) {
-        unsigned t = s_tot[lane];
+    unsigned t = s_tot[lane];                               // every warp scans the 32 warp totals itself
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned y = __shfl_up_sync(FULL, t, off);
-            if (lane >= off) t += y;
-        }
-        s_tot[lane] = t;
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned y = __shfl_up_sync(FULL, t, off);
+        if (lane >= off) t += y;
     }
-    __syncthreads();
-    const unsigned add = wid ? s_tot[wid - 1] : 0u;
-    total = s_tot[31];
-    __syncthreads();
-    return x + add;
+    total = __shfl_sync(FULL, t, 31);
+    const unsigned add = __shfl_sync(FULL, t, (wid + 31) & 31);
+    return x + (wid ? add : 0u);
 }
 
 template <bool VSMEM>
@@ -80,18 +76,22 @@ __device__ __forceinline__ bool v_test(const unsigned *V, int w) {
 template <bool VSMEM>
 __global__ void __launch_bounds__(BFS_THREADS, 1)
 bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__restrict__ adj, long long n_roots,
-           const int *__restrict__ roots, uint32_t *__restrict__ tree_bits, long long tree_words, int *__restrict__ qbuf,
+           const int *__restrict__ roots, uint32_t *__restrict__ tree_bits, long long tree_words, uint2 *__restrict__ qbuf,
            unsigned *__restrict__ gbitmap, int tagbits) {
     extern __shared__ __align__(16) unsigned bfs_smem[];
     unsigned *table = bfs_smem;
-    unsigned *start = table + BFS_HSLOTS;                  // [1025] exclusive prefix of the chunk's degrees
-    unsigned *a0s = start + BFS_THREADS + 1;               // [1024] first walk-CSR entry of the chunk's nodes
-    unsigned *s_tot = a0s + BFS_THREADS;                   // [32]
+    unsigned *start = table + BFS_HSLOTS;                  // [1025] exclusive prefix of the window's degrees
+    unsigned *a0s = start + BFS_THREADS + 1;               // [1024] first walk-CSR entry of the window's nodes
+    unsigned *s_tot = a0s + BFS_THREADS;                   // [2][32]
     const size_t bm_words = ((size_t)n_node + 31) / 32;
-    unsigned *V = VSMEM ? (s_tot + 32 + 31) : (gbitmap + (size_t)blockIdx.x * bm_words);
-    int *Q = qbuf + (size_t)blockIdx.x * (size_t)n_node;
+    unsigned *V = VSMEM ? (s_tot + 64 + 31) : (gbitmap + (size_t)blockIdx.x * bm_words);
+    // the FIFO queue holds, per discovered node, (first walk-CSR entry, degree): all a frontier node is needed for.
+    // The random indptr reads are issued when a node is APPENDED (fire and forget behind the compaction scan), so the
+    // frontier sweep itself reads the queue sequentially and one window ahead.
+    uint2 *Q = qbuf + (size_t)blockIdx.x * (size_t)n_node;
+    const unsigned *ip32 = reinterpret_cast<const unsigned *>(indptr);   // low words (nnz < 2^31, little endian)
     const int tid = threadIdx.x;
-    const unsigned tagmask = (tagbits >= 32) ? 0xffffffffu : ((1u << tagbits) - 1u);
+    const unsigned tagmask = (1u << tagbits) - 1u;
 
     for (unsigned s = tid; s < BFS_HSLOTS; s += BFS_THREADS) table[s] = BFS_EMPTY;
     for (long long r = blockIdx.x; r < n_roots; r += gridDim.x) {
@@ -100,26 +100,32 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
         for (long long i = tid; i < tree_words; i += BFS_THREADS) tb[i] = 0u;
         for (size_t i = tid; i < bm_words; i += BFS_THREADS) V[i] = 0u;
         __syncthreads();
-        if (tid == 0) { V[root >> 5] = 1u << (root & 31); Q[0] = root; }
+        if (tid == 0) {
+            V[root >> 5] = 1u << (root & 31);
+            Q[0] = make_uint2(ip32[2 * (size_t)root], ip32[2 * (size_t)root + 2] - ip32[2 * (size_t)root]);
+        }
         __syncthreads();
-        unsigned lo = 0, hi = 1, tail = 1;
+        unsigned lo = 0, hi = 1, tail = 1, flip = 0;
         while (lo < hi) {                                   // one BFS level: queue entries [lo, hi)
+            unsigned pf_i = 0xffffffffu;                    // prefetched window (valid inside a level only)
+            uint2 pf = make_uint2(0u, 0u);
             for (unsigned i = lo; i < hi;) {
                 // ---- window: the next <= 1024 frontier nodes; the chunk = the longest prefix with <= SLAB entries
                 const unsigned idx = i + tid;
-                unsigned a = 0, deg = 0;
-                if (idx < hi) {
-                    const int u = Q[idx];
-                    const long long b0 = indptr[u];
-                    a = (unsigned)b0; deg = (unsigned)(indptr[u + 1] - b0);
-                }
+                uint2 q = make_uint2(0u, 0u);
+                if (pf_i == i) q = pf;
+                else if (idx < hi) q = Q[idx];
+                const unsigned a = q.x, deg = q.y;
                 unsigned tot;
-                const unsigned incl = block_scan_incl(deg, s_tot, tot);
+                const unsigned incl = block_scan_incl(deg, s_tot + 32 * (flip ^= 1u), tot);
+                start[tid] = incl - deg; a0s[tid] = a;      // thread m's exclusive prefix is the chunk's entry count
+                if (tid == BFS_THREADS - 1) start[BFS_THREADS] = incl;
                 unsigned m = (unsigned)__syncthreads_count(idx < hi && incl <= BFS_SLAB);   // incl is non-decreasing
                 if (m == 0) m = 1;                          // one node with more than SLAB entries: a chunk of its own
-                if ((unsigned)tid < m) { start[tid] = incl - deg; a0s[tid] = a; }
-                if ((unsigned)tid == m - 1) start[m] = incl;
-                __syncthreads();
+                // the next window of this level (written during the previous level): in flight while this chunk runs
+                pf_i = i + m;
+                pf = make_uint2(0u, 0u);
+                if (pf_i + tid < hi) pf = Q[pf_i + tid];
                 const unsigned E = start[m];
                 const bool single = (m == 1);               // a node's own entries never collide: no table needed
                 for (unsigned s0 = 0; s0 < E; s0 += BFS_SLAB) {
@@ -190,15 +196,22 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                             __syncthreads();
                         }
                     }
-                    // ---- winners in entry order = FIFO order: append to the queue, set their tree bits
+                    // ---- winners in entry order = FIFO order: append (entry range of the node) to the queue, set the
+                    // tree bits.  The indptr reads fly behind the scan's barriers.
+                    unsigned qa[BFS_EPT], qb[BFS_EPT];
+#pragma unroll
+                    for (int x = 0; x < BFS_EPT; ++x) {
+                        qa[x] = qb[x] = 0;
+                        if ((wm >> x) & 1u) { qa[x] = ip32[2 * (size_t)w[x]]; qb[x] = ip32[2 * (size_t)w[x] + 2]; }
+                    }
                     unsigned ntot;
                     const unsigned cnt = (unsigned)__popc(wm);
-                    unsigned off = tail + block_scan_incl(cnt, s_tot, ntot) - cnt;
+                    unsigned off = tail + block_scan_incl(cnt, s_tot + 32 * (flip ^= 1u), ntot) - cnt;
                     unsigned word = 0xffffffffu, mask = 0;
 #pragma unroll
                     for (int x = 0; x < BFS_EPT; ++x) {
                         if (!((wm >> x) & 1u)) continue;
-                        Q[off++] = w[x];
+                        Q[off++] = make_uint2(qa[x], qb[x] - qa[x]);
                         const unsigned wi = ee[x] >> 5;
                         if (wi != word) {
                             if (mask) atomicOr(tb + word, mask);
@@ -250,7 +263,7 @@ extern "C" int gg_bfs_scratch_bytes(int64_t n_node, int64_t nnz, int64_t *bytes)
     GG_REQUIRE(bytes && n_node >= 0 && nnz >= 0, "bad arguments");
     const long long bm_bytes = (n_node + 31) / 32 * 4;
     const bool in_smem = bm_bytes <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
-    *bytes = (int64_t)gg::sm_count() * (4 * n_node + (in_smem ? 0 : bm_bytes)) + 16;
+    *bytes = (int64_t)gg::sm_count() * (8 * n_node + (in_smem ? 0 : bm_bytes)) + 16;
     return 0;
 }
 
@@ -263,14 +276,14 @@ extern "C" int gg_bfs_build(int64_t n_node, int64_t nnz, const int64_t *indptr, 
     if (n_roots == 0 || n_node == 0) return 0;
     const long long bm_bytes = (n_node + 31) / 32 * 4;
     const bool in_smem = bm_bytes <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
-    const int64_t per_cta = 4 * n_node + (in_smem ? 0 : bm_bytes);
+    const int64_t per_cta = 8 * n_node + (in_smem ? 0 : bm_bytes);
     int64_t ctas = scratch_bytes / per_cta;
     if (ctas > gg::sm_count()) ctas = gg::sm_count();
     if (ctas > n_roots) ctas = n_roots;
     GG_REQUIRE(ctas >= 1, "scratch too small");
     const int tagbits = gg::bfs_tagbits(n_node);
     GG_REQUIRE(tagbits + 10 <= 31, "graph too large for the 32-bit proposal keys");
-    int *qbuf = (int *)scratch;
+    uint2 *qbuf = (uint2 *)scratch;
     unsigned *gbm = in_smem ? nullptr : (unsigned *)(qbuf + (size_t)ctas * (size_t)n_node);
     const size_t smem = 4 * (size_t)gg::BFS_FIXED_WORDS + (in_smem ? (size_t)bm_bytes : 0);
     cudaStream_t st = (cudaStream_t)stream;

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NT, 1) train_fused_kernel(const __grid_constan
         const float lr_t = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
 #define GG_ADAM1(f)                                                                                   \
     m[k].f = __fadd_rn(__fmul_rn(m[k].f, b1), __fmul_rn(omb1, g.f));                                  \
-    v[k].f = __fadd_rn(__fmul_rn(v[k].f, b2), __fmul_rn(__fmul_rn(omb2, g.f), g.f));                  \
+    v[k].f = __fadd_rn(__fmul_rn(v[k].f, b2), __fmul_rn(__fmul_rn(g.f, g.f), omb2));                  \
     x[k].f = __fsub_rn(x[k].f, __fdiv_rn(__fmul_rn(lr_t, m[k].f), __fadd_rn(__fsqrt_rn(v[k].f), eps)));
 #define GG_ACC(f) g.f = __fadd_rn(g.f, __fadd_rn(__fmul_rn(dd[e], o[e].f), __fmul_rn(lambda, x[k].f)))
         for (int it = 0; it < iters; ++it) {
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(NT, 1) train_fused_kernel(const __grid_constan
                 *reinterpret_cast<float4 *>(E_new + at) = x[k];
                 if (cc[k] == 0) {
                     const float mm = __fadd_rn(__fmul_rn(mb[k], b1), __fmul_rn(omb1, gb));
-                    const float vv = __fadd_rn(__fmul_rn(vb[k], b2), __fmul_rn(__fmul_rn(omb2, gb), gb));
+                    const float vv = __fadd_rn(__fmul_rn(vb[k], b2), __fmul_rn(__fmul_rn(gb, gb), omb2));
                     a.m_bias[row[k]] = mm; a.v_bias[row[k]] = vv;
                     b_new[row[k]] = __fsub_rn(xb[k], __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(__fsqrt_rn(vv), eps)));
                 }
@@ -276,7 +276,7 @@ extern "C" int gg_train_loop(int32_t mode, int64_t n_rows, const int64_t *start_
     GG_REQUIRE(start_list_dev && beta1_power && beta2_power && sync_words, "null pointer");
     GG_REQUIRE(batch_size > 0 && batch_size <= GG_MAX_BATCH, "batch size out of range");
     GG_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (discriminator) or 1 (generator)");
-    GG_REQUIRE(ld > 0 && ld % 32 == 0, "ld must be a positive multiple of 32");
+    GG_REQUIRE(ld == 32 || ld == 64 || ld == 128 || ld == 256, "ld must be 32, 64, 128 or 256 (row stride in floats)");
     if (n_starts == 0) return 0;
     int dev = 0, coop = 0, per_sm = 0;
     GG_CHECK(cudaGetDevice(&dev));

@@ -281,7 +281,7 @@ __device__ __forceinline__ void adam_rows(long long n_node, int ld, float *emb, 
 // TF1.8 op order (assign m*b1; scatter_add (1-b1)*g; ... var -= lr*m/(sqrt(v)+eps)), no contraction
 #define GG_ADAM1(f)                                                                                   \
     m[k].f = __fadd_rn(__fmul_rn(m[k].f, b1), __fmul_rn(omb1, g.f));                                  \
-    v[k].f = __fadd_rn(__fmul_rn(v[k].f, b2), __fmul_rn(__fmul_rn(omb2, g.f), g.f));                  \
+    v[k].f = __fadd_rn(__fmul_rn(v[k].f, b2), __fmul_rn(__fmul_rn(g.f, g.f), omb2));                  \
     x[k].f = __fsub_rn(x[k].f, __fdiv_rn(__fmul_rn(lr_t, m[k].f), __fadd_rn(__fsqrt_rn(v[k].f), eps)));
     for (long long s0 = warp * UNR; s0 < nseg; s0 += nwarps * UNR) {
         int row[UNR], cc[UNR], slot[UNR];      // row < 0: nothing to do for this lane
@@ -321,7 +321,7 @@ __device__ __forceinline__ void adam_rows(long long n_node, int ld, float *emb, 
                 if (!PRE) { mb[k] = m_bias[row[k]]; vb[k] = v_bias[row[k]]; xb[k] = bias[row[k]]; }
                 const float gb = slot[k] >= 0 ? (COH ? __ldcg(grad_bias + slot[k]) : grad_bias[slot[k]]) : 0.0f;
                 const float mm = __fadd_rn(__fmul_rn(mb[k], b1), __fmul_rn(omb1, gb));
-                const float vv = __fadd_rn(__fmul_rn(vb[k], b2), __fmul_rn(__fmul_rn(omb2, gb), gb));
+                const float vv = __fadd_rn(__fmul_rn(vb[k], b2), __fmul_rn(__fmul_rn(gb, gb), omb2));
                 m_bias[row[k]] = mm; v_bias[row[k]] = vv;
                 bias[row[k]] = __fsub_rn(xb[k], __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(__fsqrt_rn(vv), eps)));
                 if (slot[k] >= 0) row_slot[row[k]] = -1;

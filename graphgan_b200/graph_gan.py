@@ -270,7 +270,10 @@ class GraphGAN(object):
         modes = [self.generator, self.discriminator]
         for i in range(2):
             os.makedirs(os.path.dirname(config.emb_filenames[i]) or ".", exist_ok=True)
-            io.write_embeddings(config.emb_filenames[i], self.sess.run(modes[i].embedding_matrix))
+            if config.binary_embeddings:      # [N, n_emb] fp32 straight from the device (the text form is minutes at N = 1M)
+                io.write_embeddings_binary(config.emb_filenames[i] + ".f32", modes[i])
+            if config.text_embeddings:
+                io.write_embeddings(config.emb_filenames[i], self.sess.run(modes[i].embedding_matrix))
 
     @staticmethod
     def evaluation(self):
@@ -278,9 +281,13 @@ class GraphGAN(object):
         if getattr(self, "rank", 0) != 0:
             return results
         if config.app == "link_prediction":
+            modes = [self.generator, self.discriminator]
             for i in range(2):
-                lpe = lp.LinkPredictEval(config.emb_filenames[i], config.test_filename, config.test_neg_filename,
-                                         self.n_node, config.n_emb)
+                if config.device_eval:        # from the device-resident embeddings (csrc/eval.cu): no text round trip
+                    lpe = lp.DeviceLinkPredictEval(modes[i], config.test_filename, config.test_neg_filename)
+                else:
+                    lpe = lp.LinkPredictEval(config.emb_filenames[i], config.test_filename, config.test_neg_filename,
+                                             self.n_node, config.n_emb)
                 results.append(config.modes[i] + ":" + str(lpe.eval_link_prediction()) + "\n")
         os.makedirs(os.path.dirname(config.result_filename) or ".", exist_ok=True)
         with open(config.result_filename, mode="a+") as f:

@@ -14,7 +14,8 @@
  *     synchronisation, no allocation.  Scratch is caller supplied (query *_scratch_bytes).
  *   - return 0 on success, non-zero on CUDA / argument error; gg_last_error() gives the
  *     message for the calling thread.  Nothing aborts.
- *   - embedding rows are fp32 [N, ld] with ld = round_up(n_emb, 32), zero padded.
+ *   - embedding rows are fp32 [N, ld], zero padded, with ld = 32, 64, 128 or 256 (the smallest that holds n_emb):
+ *     every entry point that takes ld rejects other values.
  *   - graph = two CSRs in the reference's adjacency-file order (src/utils.py:27-37):
  *       raw  : graph[i] as read (duplicates and self-loops kept) -> positives, sample_num
  *       walk : first occurrences only, self-loops dropped        -> BFS trees and walks
@@ -279,6 +280,20 @@ int gg_train_fused(int32_t mode, int64_t n_rows, const int64_t *start_list_dev, 
                    float *emb, float *m_emb, float *v_emb, float *bias, float *m_bias, float *v_bias, float *emb2,
                    float *bias2, float lambda, float lr, float beta1, float beta2, float eps, float *beta1_power,
                    float *beta2_power, uint64_t *sync_words, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * End-of-epoch dump and quality line on the device (csrc/eval.cu).  Replaces the text round trip of
+ * write_embeddings_to_file (graph_gan.py:293-306) -> utils.read_embeddings (utils.py:57-67) ->
+ * LinkPredictEval.eval_link_prediction (src/evaluation/link_prediction.py:19-38).
+ *   gg_pair_dot_f64  : out[k] = float64 dot of rows node_id[k], node_neighbor_id[k] (np.dot on the re-read rows)
+ *   gg_link_pred_acc : out2[0] = accuracy of (score >= np.median(score)) against labels [1]*(n/2) + [0]*(n - n/2),
+ *                      out2[1] = the median; score / out2: device float64
+ *   gg_unpad_rows    : dense [N, n_emb] fp32 copy of the padded [N, ld] rows (payload of the binary dump)
+ * ------------------------------------------------------------------------------------------ */
+int gg_pair_dot_f64(int64_t n_pairs, const int32_t *node_id, const int32_t *node_neighbor_id, const float *emb,
+                    int32_t ld, double *out, void *stream);
+int gg_link_pred_acc(int64_t n, const double *score, double *out2, void *stream);
+int gg_unpad_rows(int64_t n_node, int32_t ld, int32_t n_emb, const float *emb, float *out, void *stream);
 
 /* get_node_pairs_from_path (graph_gan.py:272-291) for a batch of recorded paths.
  * pair_ptr: device [W+1] (out, exclusive scan of per-path pair counts). */

@@ -43,7 +43,7 @@ class AdamState:
             m *= self.b1
             v *= self.b2
             m[rows] += (F(1) - self.b1) * g
-            v[rows] += (F(1) - self.b2) * g * g
+            v[rows] += (g * g) * (F(1) - self.b2)         # TF: (grad * grad) * (1 - beta2_t)
             var -= lr_t * m / (np.sqrt(v) + self.eps)
         self.b1_pow = F(self.b1_pow * self.b1)
         self.b2_pow = F(self.b2_pow * self.b2)

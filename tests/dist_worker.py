@@ -93,6 +93,23 @@ def main(mode):
         rows = [torch.empty_like(repl.emb) for _ in range(world)]
         dist.all_gather(rows, repl.emb)
         assert all(torch.equal(rows[0], r) for r in rows[1:])
+        # the C-side batch loop (gg_dp_train_steps: one collective per step, no host round trip) == step by step
+        M, Bs = 300, 64
+        ii, jj = rs.randint(0, n, M).astype(np.int32), rs.randint(0, n, M).astype(np.int32)
+        ax = ((rs.random_sample(M) < 0.5) if mode == 0 else rs.random_sample(M) * 3).astype(np.float32)
+        starts = list(range(0, M, Bs))
+        rs.shuffle(starts)
+        ra, rb = cls(n, e0, device=dev), cls(n, e0, device=dev)
+        da, db = parallel.DataParallelStep(ra), parallel.DataParallelStep(rb)
+        for s0 in starts:
+            da.step(ii[s0:s0 + Bs], jj[s0:s0 + Bs], ax[s0:s0 + Bs])
+        before = db.stats()["collectives_issued"]
+        db.train_steps(ii, jj, ax, starts, Bs)
+        for name in ("emb", "bias_t", "m_emb", "v_emb", "m_bias", "v_bias"):
+            assert torch.equal(getattr(ra, name), getattr(rb, name)), name
+        assert ra.beta1_power == rb.beta1_power and ra.step_count == rb.step_count
+        st = db.stats()
+        assert st["comm_nranks"] == world and st["collectives_issued"] - before == len(starts)
     # (3) the re-hosted trainer under torch.distributed: sharded sampling + data-parallel updates
     from graphgan_b200 import config
     from graphgan_b200.graph_gan import GraphGAN
@@ -121,10 +138,19 @@ def main(mode):
     gan.device_graph.reset_tree_mutations()
     gan.pass_counter = 0
     gan.trees, gan._tree_key = None, None
-    gan.train()
+    config.n_epochs, config.save_steps = 2, 1
+    gan.train()                       # saves (rank 0, after OR-reducing the removal bits) at the start of epoch 1
     rows = [torch.empty_like(gan.generator.emb) for _ in range(world)]
     dist.all_gather(rows, gan.generator.emb)
     assert all(torch.equal(rows[0], r) for r in rows[1:])
+    dist.barrier()
+    # (4) save -> load -> continue == uninterrupted, under sharding (every rank loads the same file)
+    config.n_epochs, config.load_model = 1, True
+    gan2 = GraphGAN(host_graph=hgc, node_embed_init_d=c.emb_d, node_embed_init_g=c.emb_g)
+    gan2.train()
+    for ma, mb in ((gan.generator, gan2.generator), (gan.discriminator, gan2.discriminator)):
+        for name in ("emb", "bias_t", "m_emb", "v_emb"):
+            assert torch.equal(getattr(ma, name), getattr(mb, name)), name
     dist.barrier()
     if rank == 0:
         print("DIST_GPU_OK")
