@@ -32,6 +32,7 @@ WORKLOADS = {
     "er_100k": ("erdos_renyi", 100_000, 10, 128),         # configs[1]
     "powerlaw_100k": ("power_law", 100_000, 10, 128),     # smoke-sized
     "powerlaw_10m": ("power_law", 10_000_000, 8, 256),    # configs[4] (per-GPU share; R is capped by the memory rule)
+    "c1_cagrqc": ("fixture", 5242, 5, 50),                # configs[0]: the shipped CA-GrQc graph + pretrain embeddings
 }
 
 
@@ -57,6 +58,11 @@ def parse():
     p.add_argument("--g-steps", type=int, default=5, help="timed generator-mode passes (0 = skip)")
     p.add_argument("--pairs", type=int, default=1 << 22, help="--phase reward: pairs per launch")
     p.add_argument("--bfs-roots", type=int, default=1184, help="--phase bfs: roots per launch (8 per SM)")
+    p.add_argument("--score-mode", default="lazy", choices=["lazy", "literal"],
+                   help="--impl reference: 'literal' recomputes the whole N x N all_score per root exactly as graph_gan.py:238 does "
+                        "(only feasible at C1); 'lazy' scores the candidates on demand (the only form that exists at N >= 1e5)")
+    p.add_argument("--adam-path", default="tma", choices=["tma", "ldg"],
+                   help="K3 sweep: cp.async.bulk (TMA) pipeline or the per-thread-load kernel (A/B; sets GG_ADAM_PATH)")
     p.add_argument("--phase", default="sample", choices=["sample", "reward", "adam", "bfs", "update"],
                    help="what to time: the D-sampling pass (the BASELINE metric) or one of the other kernels of the path")
     return p.parse_args()
@@ -65,6 +71,13 @@ def parse():
 def make_inputs(args, rank):
     from graphgan_b200 import graph as G, synth
     gen, n, deg, d = WORKLOADS[args.workload]
+    if gen == "fixture":      # BASELINE.json configs[0]: tests/golden/cagrqc.npz holds the reference's own data files
+        from tests.golden import loader
+        c = loader.load("cagrqc")
+        hg = G.HostGraph(c.train_edges, c.test_edges)
+        roots = np.flatnonzero(hg.degrees() > 0).astype(np.int32)
+        args.roots = len(roots)
+        return hg, np.asarray(c.emb_g, np.float64).astype(np.float32), roots, d
     cache = "/tmp/gg_bench_cache/%s_seed%d.npz" % (args.workload, args.seed)
     try:       # the CSR arrays of an earlier process on this box (the reference arm, another rank, an ncu pass)
         z = np.load(cache)
@@ -196,7 +209,7 @@ def _sample_roots(job):
     hg, emb, roots, par = _SH["hg"], _SH["emb"], _SH["sample"][idx], _SH["par"]
     trees = faithful.ParentTrees(_AdjView(hg.indptr, hg.adj), {int(r): par[int(i)] for i, r in zip(idx, roots)})
     F = faithful.Faithful(_GraphView(hg, roots), emb, bias_g=_SH["bias"], rng=np.random.RandomState(seed),
-                          score_mode="lazy", trees=trees)
+                          score_mode=_SH.get("score_mode", "lazy"), trees=trees)
     t0 = time.time()
     F.prepare_data_for_d(roots=[int(r) for r in roots])
     return os.getpid(), F.stats["neg_edges"], F.stats["steps"], F.stats["sum_l"], time.time() - t0
@@ -275,6 +288,7 @@ class CpuReference:
         edges = sum(done.values())
         value = sum(done[p] / busy[p] for p in busy if busy[p] > 0)
         out = {"value": value, "unit": "neg_edges/s", "cores": len(busy), "kind": "port",
+               "wall_clock_value": edges / max(dt, 1e-9), "score_mode": _SH.get("score_mode", "lazy"),
                "sample": "%d of the workload's roots (%d neg edges, %d walk steps, %d candidates), %.1f core-seconds in "
                          "%.1f s wall on %d processes; value = sum over processes of edges / busy seconds (steady-state "
                          "rate; the wall clock of a bounded sample is set by its largest root); oracle T0 lazy-score: "
@@ -298,6 +312,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     hg, emb, roots, d = make_inputs(args, 0)
+    _SH["score_mode"] = args.score_mode
     workers = os.cpu_count() or 1
     per_step_seconds = max(0.5, min(args.cpu_seconds, 150.0 / max(args.steps + args.warmup, 1)))   # whole run: a few minutes
     ref = CpuReference(hg, emb, roots, per_step_seconds, workers)
@@ -313,11 +328,15 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "sampled negative edges/sec (D-sampling pass)", "value": v,
             "unit": "neg_edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(times)) if times else None, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data_kind(args),
             "config": workload_config(args, hg, d), "cpu_baseline": last,
             "e2e": {"value": v, "unit": "neg_edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
+
+
+def data_kind(args):
+    return "reference data files (CA-GrQc, tests/golden/cagrqc.npz)" if WORKLOADS[args.workload][0] == "fixture" else "synthetic"
 
 
 def workload_config(args, hg, d):
@@ -583,7 +602,7 @@ def run_b200(args):
             "metric": "sampled negative edges/sec (D-sampling pass)", "value": float(tot[0] / (tmax[0] * 1e-3)),
             "unit": "neg_edges/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(tmax[0] / args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, hg, d),
+            "dtype": "f32", "data": data_kind(args), "config": workload_config(args, hg, d),
             "clocks": clk,
             "e2e": {"value": float(tot[1] / (tmax[1] * 1e-3)), "unit": "neg_edges/s",
                     "h2d_bytes_per_step": int(roots_pin.numel() * 4),
@@ -777,7 +796,7 @@ def run_phase(args):
                              "ms_per_step": k_ms, "scaling": "weak", "gpu_launches": args.steps,
                              "config": {"workload": "N=%d n_emb=%d (ld %d): one dense Adam sweep over E, m, v per step" % (n, d, ld),
                                         "l2_policy": "inputs larger than L2 (E, m, v = %d MB)" % (3 * n * ld * 4 >> 20)},
-                             "roofline": {"bound": "hbm", "kernel": "gg::adam_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak,
+                             "roofline": {"bound": "hbm", "kernel": "gg::adam_tma_kernel" if args.adam_path == "tma" else "gg::adam_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak,
                                           "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                                           "algorithmic_bytes_per_launch": alg, "note": "24 * N * ld bytes per step: read + write of E, m, v"}})
             else:
@@ -835,6 +854,7 @@ def main():
         os.dup2(2, 1)
     except OSError:
         _RESULT_FD = None
+    os.environ["GG_ADAM_PATH"] = args.adam_path
     if args.impl == "reference":
         return run_reference(args)
     if args.phase != "sample":

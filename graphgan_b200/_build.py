@@ -48,6 +48,16 @@ def nvcc_path():
     return p if os.path.exists(p) else None
 
 
+def build_variant(name, defines):
+    """A/B library libgraphgan_b200.<name>.so with extra -D flags (tools/variants.py); load it with GG_LIB=<path>."""
+    out_path = os.path.join(HERE, "libgraphgan_b200.%s.so" % name)
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-D%s" % d for d in defines] + ["-o", out_path] + sources()
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + out.stdout)
+    return out_path
+
+
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB

@@ -83,8 +83,8 @@ def lib():
     """Load (building first if the .so is absent).  Raises GGError on any failure."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB
-        if _build.stale():      # missing, or built from other sources than the tree holds (content hash)
+        path = os.environ.get("GG_LIB") or _build.LIB      # GG_LIB: an A/B variant built by tools/variants.py
+        if path == _build.LIB and _build.stale():      # missing, or built from other sources than the tree holds (content hash)
             if os.path.exists(path) and _build.nvcc_path() is None:
                 raise GGError("libgraphgan_b200.so was built from different sources and there is no nvcc to rebuild it")
             try:

@@ -11,6 +11,9 @@
 // chains of the update are what the warps wait on -- ncu: fixed-latency dependency stalls -- so occupancy beats
 // deeper unrolling: 4 in flight at 112 registers ran at 45 % of DRAM peak); the row -> gradient-slot map
 // written by gg_pair_grad tells whether the row has a gradient, and is reset here.
+#include <stdlib.h>
+#include <string.h>
+
 #include "update_dev.cuh"
 
 namespace gg {
@@ -25,6 +28,142 @@ __global__ void __launch_bounds__(256, 4) adam_kernel(long long n_node, int ld, 
     adam_rows<false, 2>(n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, grad_rows, grad_bias, row_slot, lr_t, b1, b2, eps);
 }
 
+// ---------------------------------------------------------------- the same sweep with TMA bulk copies (Blackwell)
+// The sweep is a pure stream (24 * N * ld bytes per step), so it is fed by the copy engine instead of per-thread loads:
+// one elected thread issues cp.async.bulk (global -> shared, completion on an mbarrier) for a tile of E, m and v, all
+// 256 threads update the tile in shared memory (the identical per-element operation sequence as adam_rows), and one
+// thread sends it back with cp.async.bulk (shared -> global).  Two tiles load, one computes and one stores per CTA, so the
+// IEEE div / sqrt chains of one tile overlap the transfers of the next ones with no registers spent on the pipeline.
+constexpr int ADAM_TILE = 2048;                   // floats per array per tile (8 KB): 64 / 32 / 16 / 8 rows
+constexpr int ADAM_STAGES = 4;
+constexpr int ADAM_THREADS = 256;
+constexpr size_t ADAM_TMA_SMEM = (size_t)ADAM_STAGES * 3 * ADAM_TILE * 4 + 64;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS, 2)
+adam_tma_kernel(long long n_node, int ld, float *__restrict__ emb, float *__restrict__ m_emb, float *__restrict__ v_emb,
+                float *__restrict__ bias, float *__restrict__ m_bias, float *__restrict__ v_bias,
+                const float *__restrict__ grad_rows, const float *__restrict__ grad_bias, int *__restrict__ row_slot,
+                float lr_t, float b1, float b2, float eps) {
+    extern __shared__ __align__(128) unsigned char adam_smem[];
+    float *buf = reinterpret_cast<float *>(adam_smem);                       // [STAGES][3][TILE]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(adam_smem + (size_t)ADAM_STAGES * 3 * ADAM_TILE * 4);
+    const int tid = threadIdx.x;
+    const long long total = n_node * (long long)ld;
+    const long long n_tiles = (total + ADAM_TILE - 1) / ADAM_TILE;
+    const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+    const int rows_per_tile = ADAM_TILE / ld;
+    if (tid == 0) {
+        for (int s = 0; s < ADAM_STAGES; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long k) {               // thread 0: the three loads of my k-th tile
+        const int s = (int)(k % ADAM_STAGES);
+        const long long t = blockIdx.x + k * gridDim.x;
+        const long long at = t * ADAM_TILE;
+        const unsigned bytes = (unsigned)(((total - at) < ADAM_TILE ? (total - at) : ADAM_TILE) * 4);
+        float *sb = buf + (size_t)s * 3 * ADAM_TILE;
+        mbar_expect_tx(full + s, 3 * bytes);
+        bulk_g2s(sb, emb + at, bytes, full + s);
+        bulk_g2s(sb + ADAM_TILE, m_emb + at, bytes, full + s);
+        bulk_g2s(sb + 2 * ADAM_TILE, v_emb + at, bytes, full + s);
+    };
+    if (tid == 0)
+        for (long long k = 0; k < ADAM_STAGES - 2 && k < my_tiles; ++k) issue(k);
+    for (long long k = 0; k < my_tiles; ++k) {
+        const int s = (int)(k % ADAM_STAGES);
+        const unsigned parity = (unsigned)((k / ADAM_STAGES) & 1);
+        if (tid == 0 && k + ADAM_STAGES - 2 < my_tiles) {
+            // the stage about to be refilled held tile k - 2, stored two iterations ago: the copy engine must have
+            // finished READING it; the store of tile k - 1 may still be in flight (one pending group allowed)
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            issue(k + ADAM_STAGES - 2);
+        }
+        const long long t = blockIdx.x + k * gridDim.x;
+        const long long at = t * ADAM_TILE;
+        const int nfl = (int)((total - at) < ADAM_TILE ? (total - at) : ADAM_TILE);
+        const long long row0 = at / ld;
+        float *sx = buf + (size_t)s * 3 * ADAM_TILE, *sm = sx + ADAM_TILE, *sv = sx + 2 * ADAM_TILE;
+        // slots of my rows (independent of the tile data: issued before the wait)
+        int slot[ADAM_TILE / (4 * ADAM_THREADS)];
+#pragma unroll
+        for (int p = 0; p < ADAM_TILE / (4 * ADAM_THREADS); ++p) {
+            const int e = 4 * (tid + ADAM_THREADS * p);
+            slot[p] = (e < nfl) ? row_slot[row0 + e / ld] : -1;
+        }
+        mbar_wait(full + s, parity);
+#define GG_ADAM_E(f)                                                                                  \
+    m4.f = __fadd_rn(__fmul_rn(m4.f, b1), __fmul_rn(omb1, g.f));                                      \
+    v4.f = __fadd_rn(__fmul_rn(v4.f, b2), __fmul_rn(__fmul_rn(g.f, g.f), omb2));                      \
+    x4.f = __fsub_rn(x4.f, __fdiv_rn(__fmul_rn(lr_t, m4.f), __fadd_rn(__fsqrt_rn(v4.f), eps)));
+#pragma unroll
+        for (int p = 0; p < ADAM_TILE / (4 * ADAM_THREADS); ++p) {
+            const int e = 4 * (tid + ADAM_THREADS * p);
+            if (e >= nfl) continue;
+            const int r = e / ld, c = e - r * ld;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (slot[p] >= 0) g = *reinterpret_cast<const float4 *>(grad_rows + (size_t)slot[p] * ld + c);
+            float4 x4 = *reinterpret_cast<float4 *>(sx + e), m4 = *reinterpret_cast<float4 *>(sm + e),
+                   v4 = *reinterpret_cast<float4 *>(sv + e);
+            GG_ADAM_E(x) GG_ADAM_E(y) GG_ADAM_E(z) GG_ADAM_E(w)
+            *reinterpret_cast<float4 *>(sx + e) = x4;
+            *reinterpret_cast<float4 *>(sm + e) = m4;
+            *reinterpret_cast<float4 *>(sv + e) = v4;
+            if (c == 0) {                         // this thread owns the row's bias (and its slot, cleared below)
+                const long long row = row0 + r;
+                const float gb = slot[p] >= 0 ? grad_bias[slot[p]] : 0.0f;
+                const float mm = __fadd_rn(__fmul_rn(m_bias[row], b1), __fmul_rn(omb1, gb));
+                const float vv = __fadd_rn(__fmul_rn(v_bias[row], b2), __fmul_rn(__fmul_rn(gb, gb), omb2));
+                m_bias[row] = mm; v_bias[row] = vv;
+                bias[row] = __fsub_rn(bias[row], __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(__fsqrt_rn(vv), eps)));
+            }
+        }
+#undef GG_ADAM_E
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // my shared-memory writes -> visible to the copy engine
+        __syncthreads();                                                 // (also: every thread has read its rows' slots)
+#pragma unroll
+        for (int p = 0; p < ADAM_TILE / (4 * ADAM_THREADS); ++p) {
+            const int e = 4 * (tid + ADAM_THREADS * p);
+            if (e < nfl && slot[p] >= 0 && e % ld == 0) row_slot[row0 + e / ld] = -1;
+        }
+        if (tid == 0) {
+            bulk_s2g(emb + at, sx, (unsigned)nfl * 4);
+            bulk_s2g(m_emb + at, sm, (unsigned)nfl * 4);
+            bulk_s2g(v_emb + at, sv, (unsigned)nfl * 4);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        (void)rows_per_tile;
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA retires
+}
+
 }  // namespace
 }  // namespace gg
 
@@ -33,9 +172,23 @@ extern "C" int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_em
                              const float *grad_rows, const float *grad_bias, int32_t *row_slot, float lr_t, float beta1,
                              float beta2, float eps, void *stream) {
     (void)n_unique; (void)uniq_ids;
+    static int use_tma = -1;       // GG_ADAM_PATH=ldg selects the per-thread-load sweep (kept for the A/B measurement)
+    if (use_tma < 0) {
+        const char *e = getenv("GG_ADAM_PATH");
+        use_tma = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
+    }
     GG_REQUIRE(emb && m_emb && v_emb && bias && m_bias && v_bias && grad_rows && grad_bias && row_slot, "null pointer");
     GG_REQUIRE(ld == 32 || ld == 64 || ld == 128 || ld == 256, "ld must be 32, 64, 128 or 256 (row stride in floats)");
     if (n_node == 0) return 0;
+    if (use_tma) {
+        const long long n_tiles = (n_node * (long long)ld + gg::ADAM_TILE - 1) / gg::ADAM_TILE;
+        long long blocks = (long long)gg::sm_count() * 2;
+        if (blocks > n_tiles) blocks = n_tiles;
+        GG_CHECK(cudaFuncSetAttribute(gg::adam_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gg::ADAM_TMA_SMEM));
+        gg::adam_tma_kernel<<<(unsigned)blocks, gg::ADAM_THREADS, gg::ADAM_TMA_SMEM, (cudaStream_t)stream>>>(
+            n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, grad_rows, grad_bias, row_slot, lr_t, beta1, beta2, eps);
+        return gg::check_cuda(cudaGetLastError(), "adam (TMA) kernel launch");
+    }
     const int q = ld / 4;                                                       // float4 per row
     const long long nseg = q >= 32 ? n_node * (q / 32) : (n_node + 32 / q - 1) / (32 / q);   // 512-byte segments
     long long blocks = (nseg + 2 * 8 - 1) / (2 * 8);                            // 8 warps x 2 segments in flight

@@ -83,6 +83,7 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
     unsigned *start = table + BFS_HSLOTS;                  // [1025] exclusive prefix of the window's degrees
     unsigned *a0s = start + BFS_THREADS + 1;               // [1024] first walk-CSR entry of the window's nodes
     unsigned *s_tot = a0s + BFS_THREADS;                   // [2][32]
+    unsigned *s_win = s_tot + 64;                          // "this slab discovered something" flag
     const size_t bm_words = ((size_t)n_node + 31) / 32;
     unsigned *V = VSMEM ? (s_tot + 64 + 31) : (gbitmap + (size_t)blockIdx.x * bm_words);
     // the FIFO queue holds, per discovered node, (first walk-CSR entry, degree): all a frontier node is needed for.
@@ -109,120 +110,149 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
         while (lo < hi) {                                   // one BFS level: queue entries [lo, hi)
             unsigned pf_i = 0xffffffffu;                    // prefetched window (valid inside a level only)
             uint2 pf = make_uint2(0u, 0u);
-            for (unsigned i = lo; i < hi;) {
-                // ---- window: the next <= 1024 frontier nodes; the chunk = the longest prefix with <= SLAB entries
-                const unsigned idx = i + tid;
+            for (unsigned wbase = lo; wbase < hi; wbase += BFS_THREADS) {
+                // ---- window: the next <= 1024 frontier nodes; ONE scan numbers all their adjacency entries, the
+                // chunks (<= SLAB entries each) are then cut out of that numbering
+                const unsigned nvalid = (hi - wbase) < (unsigned)BFS_THREADS ? (hi - wbase) : (unsigned)BFS_THREADS;
                 uint2 q = make_uint2(0u, 0u);
-                if (pf_i == i) q = pf;
-                else if (idx < hi) q = Q[idx];
-                const unsigned a = q.x, deg = q.y;
-                unsigned tot;
-                const unsigned incl = block_scan_incl(deg, s_tot + 32 * (flip ^= 1u), tot);
-                start[tid] = incl - deg; a0s[tid] = a;      // thread m's exclusive prefix is the chunk's entry count
-                if (tid == BFS_THREADS - 1) start[BFS_THREADS] = incl;
-                unsigned m = (unsigned)__syncthreads_count(idx < hi && incl <= BFS_SLAB);   // incl is non-decreasing
-                if (m == 0) m = 1;                          // one node with more than SLAB entries: a chunk of its own
-                // the next window of this level (written during the previous level): in flight while this chunk runs
-                pf_i = i + m;
-                pf = make_uint2(0u, 0u);
+                if (pf_i == wbase) q = pf;
+                else if ((unsigned)tid < nvalid) q = Q[wbase + tid];
+                pf_i = wbase + BFS_THREADS;                 // the next window of this level (written during the previous
+                pf = make_uint2(0u, 0u);                    // level): in flight while this one is processed
                 if (pf_i + tid < hi) pf = Q[pf_i + tid];
-                const unsigned E = start[m];
-                const bool single = (m == 1);               // a node's own entries never collide: no table needed
-                for (unsigned s0 = 0; s0 < E; s0 += BFS_SLAB) {
-                    const unsigned k0 = s0 + (unsigned)tid * BFS_EPT;
-                    unsigned j0 = 0;
-                    if (!single && k0 < E) {                // owner of entry k0: last j with start[j] <= k0
-                        unsigned l = 0, h = m - 1;
-                        while (l < h) {
-                            const unsigned mid = (l + h + 1) >> 1;
-                            if (start[mid] <= k0) l = mid; else h = mid - 1;
-                        }
-                        j0 = l;
-                    }
-                    unsigned ee[BFS_EPT], key[BFS_EPT];
-                    int w[BFS_EPT];
-                    {
-                        unsigned jj = j0;
+                unsigned tot;
+                const unsigned incl = block_scan_incl(q.y, s_tot + 32 * (flip ^= 1u), tot);
+                start[tid] = incl - q.y; a0s[tid] = q.x;
+                if (tid == BFS_THREADS - 1) start[BFS_THREADS] = incl;
+                __syncthreads();
+                unsigned jlo = 0;
+                while (jlo < nvalid) {                      // chunks of consecutive frontier nodes
+                    const unsigned base = start[jlo];
+                    unsigned m = (unsigned)__syncthreads_count((unsigned)tid >= jlo && (unsigned)tid < nvalid &&
+                                                               start[tid + 1] - base <= BFS_SLAB);   // a prefix of [jlo, nvalid)
+                    if (m == 0) m = 1;                      // one node with more than SLAB entries: a chunk of its own
+                    if (tid == 0) *s_win = 0u;              // (the previous chunk's readers are behind the barrier above)
+                    const unsigned Kend = start[jlo + m];   // entries [base, Kend) in the window's numbering
+                    const bool single = (m == 1);           // a node's own entries never collide: no table needed
+                    for (unsigned s0 = base; s0 < Kend; s0 += BFS_SLAB) {
+                        const unsigned K0 = s0 + (unsigned)tid * BFS_EPT;
+                        unsigned ee[BFS_EPT], key[BFS_EPT];
+                        int w[BFS_EPT];
 #pragma unroll
-                        for (int x = 0; x < BFS_EPT; ++x) {
-                            const unsigned k = k0 + x;
-                            ee[x] = 0xffffffffu; key[x] = 0;
-                            if (k < E) {
-                                while (jj + 1 < m && start[jj + 1] <= k) ++jj;
-                                ee[x] = a0s[jj] + (k - start[jj]);
-                                key[x] = jj << tagbits;
+                        for (int x = 0; x < BFS_EPT; ++x) { ee[x] = 0xffffffffu; key[x] = 0; }
+                        if (K0 < Kend) {
+                            unsigned j = jlo;
+                            if (!single) {                  // owner of entry K0: last j in the chunk with start[j] <= K0
+                                unsigned l = jlo, h = jlo + m - 1;
+                                while (l < h) {
+                                    const unsigned mid = (l + h + 1) >> 1;
+                                    if (start[mid] <= K0) l = mid; else h = mid - 1;
+                                }
+                                j = l;
                             }
-                        }
-                    }
+                            unsigned nxt = start[j + 1];
+                            if (K0 + BFS_EPT <= nxt) {      // all my entries belong to one node (the common case)
+                                const unsigned e0 = a0s[j] + (K0 - start[j]);
 #pragma unroll
-                    for (int x = 0; x < BFS_EPT; ++x) w[x] = (ee[x] != 0xffffffffu) ? __ldg(adj + ee[x]) : -1;
-                    unsigned cm = 0;                        // candidate entries: head not discovered yet
+                                for (int x = 0; x < BFS_EPT; ++x) { ee[x] = e0 + x; key[x] = (j - jlo) << tagbits; }
+                            } else {
 #pragma unroll
-                    for (int x = 0; x < BFS_EPT; ++x)
-                        if (w[x] >= 0 && !v_test<VSMEM>(V, w[x])) cm |= 1u << x;
-                    unsigned wm = 0;                        // winners: the tree edges among my entries
-                    if (single) {
-                        wm = cm;
-#pragma unroll
-                        for (int x = 0; x < BFS_EPT; ++x)
-                            if ((cm >> x) & 1u) atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
-                    } else {
-#pragma unroll
-                        for (int x = 0; x < BFS_EPT; ++x) key[x] |= ((unsigned)w[x] >> BFS_HBITS) & tagmask;
-                        unsigned pend = cm;
-                        for (;;) {
-#pragma unroll
-                            for (int x = 0; x < BFS_EPT; ++x)
-                                if ((pend >> x) & 1u) atomicMin(table + ((unsigned)w[x] & (BFS_HSLOTS - 1)), key[x]);
-                            __syncthreads();
-                            unsigned still = 0;
-#pragma unroll
-                            for (int x = 0; x < BFS_EPT; ++x) {
-                                if (!((pend >> x) & 1u)) continue;
-                                const unsigned t = table[(unsigned)w[x] & (BFS_HSLOTS - 1)];
-                                if (t == key[x]) {
-                                    wm |= 1u << x;
-                                    atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
-                                } else if ((t & tagmask) != (key[x] & tagmask)) {
-                                    still |= 1u << x;       // the slot went to another head: try again
+                                for (int x = 0; x < BFS_EPT; ++x) {
+                                    const unsigned K = K0 + x;
+                                    if (K < Kend) {
+                                        while (K >= nxt) { ++j; nxt = start[j + 1]; }   // (skips empty nodes; K < Kend bounds j)
+                                        ee[x] = a0s[j] + (K - start[j]);
+                                        key[x] = (j - jlo) << tagbits;
+                                    }
                                 }
                             }
-                            const int any = __syncthreads_or(still != 0u);
-#pragma unroll
-                            for (int x = 0; x < BFS_EPT; ++x)
-                                if ((pend >> x) & 1u) table[(unsigned)w[x] & (BFS_HSLOTS - 1)] = BFS_EMPTY;
-                            pend = still;
-                            if (!any) break;
-                            __syncthreads();
                         }
-                    }
-                    // ---- winners in entry order = FIFO order: append (entry range of the node) to the queue, set the
-                    // tree bits.  The indptr reads fly behind the scan's barriers.
-                    unsigned qa[BFS_EPT], qb[BFS_EPT];
 #pragma unroll
-                    for (int x = 0; x < BFS_EPT; ++x) {
-                        qa[x] = qb[x] = 0;
-                        if ((wm >> x) & 1u) { qa[x] = ip32[2 * (size_t)w[x]]; qb[x] = ip32[2 * (size_t)w[x] + 2]; }
-                    }
-                    unsigned ntot;
-                    const unsigned cnt = (unsigned)__popc(wm);
-                    unsigned off = tail + block_scan_incl(cnt, s_tot + 32 * (flip ^= 1u), ntot) - cnt;
-                    unsigned word = 0xffffffffu, mask = 0;
+                        for (int x = 0; x < BFS_EPT; ++x) w[x] = (ee[x] != 0xffffffffu) ? __ldg(adj + ee[x]) : -1;
+                        unsigned cm = 0;                    // candidate entries: head not discovered yet
 #pragma unroll
-                    for (int x = 0; x < BFS_EPT; ++x) {
-                        if (!((wm >> x) & 1u)) continue;
-                        Q[off++] = make_uint2(qa[x], qb[x] - qa[x]);
-                        const unsigned wi = ee[x] >> 5;
-                        if (wi != word) {
-                            if (mask) atomicOr(tb + word, mask);
-                            word = wi; mask = 0;
+                        for (int x = 0; x < BFS_EPT; ++x)
+                            if (w[x] >= 0 && !v_test<VSMEM>(V, w[x])) cm |= 1u << x;
+                        unsigned wm = 0;                    // winners: the tree edges among my entries
+                        int anyw;
+                        if (single) {
+                            wm = cm;
+                            if (cm) {
+#pragma unroll
+                                for (int x = 0; x < BFS_EPT; ++x)
+                                    if ((cm >> x) & 1u) atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
+                            }
+                            anyw = __syncthreads_or(wm != 0u);
+                        } else {
+                            unsigned pend = cm;
+                            if (cm) {
+#pragma unroll
+                                for (int x = 0; x < BFS_EPT; ++x) key[x] |= ((unsigned)w[x] >> BFS_HBITS) & tagmask;
+                            }
+                            for (;;) {
+                                if (pend) {
+#pragma unroll
+                                    for (int x = 0; x < BFS_EPT; ++x)
+                                        if ((pend >> x) & 1u) atomicMin(table + ((unsigned)w[x] & (BFS_HSLOTS - 1)), key[x]);
+                                }
+                                __syncthreads();
+                                unsigned still = 0;
+                                if (pend) {
+#pragma unroll
+                                    for (int x = 0; x < BFS_EPT; ++x) {
+                                        if (!((pend >> x) & 1u)) continue;
+                                        const unsigned t = table[(unsigned)w[x] & (BFS_HSLOTS - 1)];
+                                        if (t == key[x]) {
+                                            wm |= 1u << x;
+                                            atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
+                                        } else if ((t & tagmask) != (key[x] & tagmask)) {
+                                            still |= 1u << x;   // the slot went to another head: try again
+                                        }
+                                    }
+                                    if (wm) *s_win = 1u;
+                                }
+                                const int any = __syncthreads_or(still != 0u);
+                                if (pend) {
+#pragma unroll
+                                    for (int x = 0; x < BFS_EPT; ++x)
+                                        if ((pend >> x) & 1u) table[(unsigned)w[x] & (BFS_HSLOTS - 1)] = BFS_EMPTY;
+                                }
+                                pend = still;
+                                if (!any) break;
+                                __syncthreads();
+                            }
+                            anyw = (int)*s_win;
                         }
-                        mask |= 1u << (ee[x] & 31);
+                        if (!anyw) continue;                // (uniform) nothing discovered by this slab: no compaction
+                        // ---- winners in entry order = FIFO order: append (entry range of the node) to the queue, set the
+                        // tree bits.  The indptr reads fly behind the scan's barrier.
+                        unsigned qa[BFS_EPT], qb[BFS_EPT];
+#pragma unroll
+                        for (int x = 0; x < BFS_EPT; ++x) {
+                            qa[x] = qb[x] = 0;
+                            if ((wm >> x) & 1u) { qa[x] = ip32[2 * (size_t)w[x]]; qb[x] = ip32[2 * (size_t)w[x] + 2]; }
+                        }
+                        unsigned ntot;
+                        const unsigned cnt = (unsigned)__popc(wm);
+                        unsigned off = tail + block_scan_incl(cnt, s_tot + 32 * (flip ^= 1u), ntot) - cnt;
+                        unsigned word = 0xffffffffu, mask = 0;
+#pragma unroll
+                        for (int x = 0; x < BFS_EPT; ++x) {
+                            if (!((wm >> x) & 1u)) continue;
+                            Q[off++] = make_uint2(qa[x], qb[x] - qa[x]);
+                            const unsigned wi = ee[x] >> 5;
+                            if (wi != word) {
+                                if (mask) atomicOr(tb + word, mask);
+                                word = wi; mask = 0;
+                            }
+                            mask |= 1u << (ee[x] & 31);
+                        }
+                        if (mask) atomicOr(tb + word, mask);
+                        tail += ntot;
+                        if (single && s0 + BFS_SLAB < Kend) __syncthreads();   // next slab of the same node: *s_win is not used
                     }
-                    if (mask) atomicOr(tb + word, mask);
-                    tail += ntot;
+                    jlo += m;
                 }
-                i += m;
             }
             __syncthreads();                                // the queue entries appended above are read next
             lo = hi; hi = tail;

@@ -43,6 +43,30 @@ __device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const 
                                                    long long a1, bool cached, int *ids, float *sc, int lane, int &n, float &m) {
     if (a1 <= a0) return;
     const unsigned lt = (1u << lane) - 1u;
+    if (a1 - a0 <= 64) {
+        // short list (the common case): adjacency entries and their bitmap words are loaded together -- the step's
+        // dependent chain is indptr -> {bits, adj} -> rows instead of indptr -> bits -> adj -> rows
+        const long long e0 = a0 + lane, e1 = a0 + 32 + lane;
+        const bool in0 = e0 < a1, in1 = e1 < a1;
+        const unsigned w0 = in0 ? __ldg(tb + (e0 >> 5)) : 0u, w1 = in1 ? __ldg(tb + (e1 >> 5)) : 0u;
+        const int v0 = in0 ? __ldg(d.adj + e0) : -1, v1 = in1 ? __ldg(d.adj + e1) : -1;
+        const float c0 = (cached && in0) ? __ldg(d.edge_score + e0) : 0.0f, c1 = (cached && in1) ? __ldg(d.edge_score + e1) : 0.0f;
+        const bool s0 = in0 && ((w0 >> (e0 & 31)) & 1u), s1 = in1 && ((w1 >> (e1 & 31)) & 1u);
+        const unsigned m0 = __ballot_sync(FULL, s0), m1 = __ballot_sync(FULL, s1);
+        if (s0) {
+            const int pos = n + __popc(m0 & lt);
+            ids[pos] = v0;
+            if (cached) { sc[pos] = c0; m = fmaxf(m, c0); }
+        }
+        n += __popc(m0);
+        if (s1) {
+            const int pos = n + __popc(m1 & lt);
+            ids[pos] = v1;
+            if (cached) { sc[pos] = c1; m = fmaxf(m, c1); }
+        }
+        n += __popc(m1);
+        return;
+    }
     const long long wfirst = a0 >> 5, wlast = (a1 - 1) >> 5;
     for (long long wb = wfirst; wb <= wlast; wb += 32) {
         const long long wi = wb + lane;
@@ -193,7 +217,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             __syncwarp();
             cyc[2] += (unsigned int)(clock64() - t_c);
         }
-        cyc[step == 0 ? 3 : (step == 1 ? 4 : 5)] += (unsigned int)(clock64() - t_step);
+        cyc[step == 0 ? 3 : (step == 1 ? 4 : 5)] += (unsigned int)(clock64() - t_step);   // (dynamic index: keeps the counters in local memory, off the register budget)
         if (step == 0) fedge = (int)(a0 + idx);  // every walk-CSR neighbour of the root is its child
         if (prow && lane == 0 && plen < d.max_path) prow[plen] = nxt;
         ++plen;
@@ -245,7 +269,7 @@ __global__ void root_step_kernel(const __grid_constant__ gg_walk_desc d) {
 constexpr int S1_SINGLES = 8192, S1_CHUNK = 16;
 
 template <int CPL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) step1_cdf_kernel(const __grid_constant__ gg_walk_desc d) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) step1_cdf_kernel(const __grid_constant__ gg_walk_desc d) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
@@ -301,7 +325,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) step1_cdf_kernel(const 
 
 // ---------------------------------------------------------------- order-free (Philox) kernel
 template <int CPL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) walk_kernel(const __grid_constant__ gg_walk_desc d) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) walk_kernel(const __grid_constant__ gg_walk_desc d) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
@@ -488,7 +512,7 @@ __global__ void emit_rows_kernel(long long n_roots, const int *roots, const long
     }
 }
 
-int grid_ctas() { return sm_count() * 3; }
+int grid_ctas() { return sm_count() * WALK_MIN_CTAS; }
 
 }  // namespace
 }  // namespace gg
@@ -513,6 +537,18 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
     GG_REQUIRE(d.n_walks < (1ll << 32), "too many walks in one call");
     GG_REQUIRE(d.max_cand > 0 && d.scratch, "scratch missing");
     GG_REQUIRE(!d.root_q || d.rq_ptr, "root_q needs rq_ptr");
+    // optional groups: all of a group or none of it (a half-filled descriptor is an argument error, not a fault)
+    GG_REQUIRE(d.max_path >= 0 && (d.max_path == 0 || (d.paths && d.path_len)), "max_path > 0 needs paths and path_len");
+    GG_REQUIRE(d.phase_mask >= 0 && d.phase_mask <= 3, "phase_mask must be 0..3");
+    GG_REQUIRE(d.update_ratio >= 0.0, "update_ratio must be >= 0");
+    GG_REQUIRE(d.rng_mode == GG_RNG_PHILOX || d.rng_mode == GG_RNG_STREAM, "unknown rng_mode");
+    {
+        const bool any_s1 = d.s1_q || d.s1_ids || d.s1_cnt || d.s1_n || d.s1_ptr || d.s1_slot || d.first_idx || d.s1_order;
+        GG_REQUIRE(!any_s1 || (d.s1_q && d.s1_ids && d.s1_cnt && d.s1_n && d.s1_ptr && d.s1_slot && d.first_idx && d.s1_nq > 0),
+                   "depth-1 reuse: s1_q, s1_ids, s1_cnt, s1_n, s1_ptr, s1_slot, first_idx and s1_nq go together");
+        GG_REQUIRE(!any_s1 || d.rng_mode == GG_RNG_PHILOX, "depth-1 reuse needs GG_RNG_PHILOX");
+        GG_REQUIRE(!d.walk_order || d.rng_mode == GG_RNG_PHILOX, "walk_order needs GG_RNG_PHILOX");
+    }
     GG_REQUIRE(!d.edge_score || (d.hub_threshold > 0 && d.hub_threshold < gg::SMEM_CAP), "hub_threshold out of range");
     cudaStream_t st = (cudaStream_t)stream;
     GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));

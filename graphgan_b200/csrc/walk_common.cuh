@@ -6,12 +6,25 @@
 
 namespace gg {
 
+// Tuning knobs (compile-time; tools/variants.py builds A/B libraries with -DGG_...): the walk kernels are latency
+// bound, so the trade is occupancy (registers, shared memory per warp) against loads in flight per warp (unrolling)
+// and against instruction footprint (the hot path must stay near the 32 KB L1.5 instruction cache).
+#ifndef GG_SC_CAP
+#define GG_SC_CAP 2048
+#endif
+#ifndef GG_UNR
+#define GG_UNR 4
+#endif
+#ifndef GG_WALK_MIN_CTAS
+#define GG_WALK_MIN_CTAS 3
+#endif
 constexpr int WARPS_PER_CTA = 8;
+constexpr int WALK_MIN_CTAS = GG_WALK_MIN_CTAS;   // CTAs per SM the walk kernels are compiled and launched for
 constexpr int ID_CAP = 320;    // candidate ids per warp kept in shared memory (longer lists: global scratch)
-constexpr int SC_CAP = 2048;   // candidate scores per warp kept in shared memory
+constexpr int SC_CAP = GG_SC_CAP;   // candidate scores per warp kept in shared memory
 constexpr int SMEM_CAP = ID_CAP;
 constexpr int WALK_SMEM_PER_WARP = SC_CAP * 4 + ID_CAP * 4;
-constexpr int UNR = 4;         // tiles of 32 candidates in flight per pass iteration
+constexpr int UNR = GG_UNR;    // tiles of 32 candidates in flight per pass iteration
 
 // cur row in registers: lane (grp, g) holds float4 chunks g, g+8, ... (replicated over the 4 groups)
 template <int CPL>
@@ -187,7 +200,7 @@ __device__ __forceinline__ int cdf_pick(const float *sc, int n, float S, double 
 // Long lists (global scratch): running total after EVERY tile goes to `tiles` (the warp's idle shared score buffer
 // viewed as doubles), so the draw can locate its tile among hundreds without a linear scan.
 __device__ __forceinline__ double cdf_total_tiles(const float *sc, int n, float S, int lane, double *tiles) {
-    constexpr int U = 16;
+    constexpr int U = 8;
     double total = 0.0;
     for (int t0 = 0; t0 < n; t0 += 32 * U) {
         float e[U];
@@ -220,22 +233,27 @@ __device__ __forceinline__ int cdf_pick_tiles(const float *sc, int n, float S, d
     return n - 1;
 }
 
-__device__ __forceinline__ int choose_index(float *sc, int n, float m, double u, int lane, double *tiles = nullptr) {
+// lists longer than the shared score buffer (global scratch): rare, so kept out of line and modestly unrolled -- the
+// walk kernel's instruction footprint is what its warps stall on otherwise (ncu: "no instruction")
+static __device__ __noinline__ int choose_index_long(float *sc, int n, float m, double u, int lane, double *tiles) {
     float S;
     double car[2], total;
-    if (n > SC_CAP && tiles && ((n + 31) >> 5) <= SC_CAP / 2) {
-        // the list lives in global scratch: 16 tiles in flight per pass, per-tile totals in shared memory
-        S = softmax_exp_sum<16>(sc, n, m, lane);
+    if (tiles && ((n + 31) >> 5) <= SC_CAP / 2) {
+        // per-tile running totals in the (idle) shared score buffer: the draw finds its tile among hundreds directly
+        S = softmax_exp_sum<8>(sc, n, m, lane);
         total = cdf_total_tiles(sc, n, S, lane, tiles);
         return cdf_pick_tiles(sc, n, S, total, u, lane, tiles);
     }
-    if (n > SC_CAP) {
-        S = softmax_exp_sum<16>(sc, n, m, lane);
-        total = cdf_total<16>(sc, n, S, lane, car);
-    } else {
-        S = softmax_exp_sum(sc, n, m, lane);
-        total = cdf_total(sc, n, S, lane, car);
-    }
+    S = softmax_exp_sum<8>(sc, n, m, lane);
+    total = cdf_total<8>(sc, n, S, lane, car);
+    return cdf_pick(sc, n, S, total, u, lane, car);
+}
+
+__device__ __forceinline__ int choose_index(float *sc, int n, float m, double u, int lane, double *tiles = nullptr) {
+    if (n > SC_CAP) return choose_index_long(sc, n, m, u, lane, tiles);
+    double car[2];
+    const float S = softmax_exp_sum(sc, n, m, lane);
+    const double total = cdf_total(sc, n, S, lane, car);
     return cdf_pick(sc, n, S, total, u, lane, car);
 }
 

@@ -50,7 +50,8 @@ def main():
         doc = json.load(open(path))
     except (OSError, ValueError):
         doc = {}
-    h = _build.source_hash()
+    # the hash of the sources the CAPTURED library was built from: pass it (4th argument) when the tree has moved on
+    h = sys.argv[4] if len(sys.argv) > 4 else _build.source_hash()
     if doc.get("source_hash") != h:
         doc = {"source_hash": h, "kernels": {}, "detail": {}}
     k1 = ["hub_score_kernel", "root_cdf_kernel", "root_step_kernel", "step1_cdf_kernel", "walk_kernel"]
