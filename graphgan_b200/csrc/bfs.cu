@@ -39,6 +39,7 @@ constexpr unsigned BFS_SLAB = BFS_THREADS * BFS_EPT;       // 8192 entries
 constexpr int BFS_HBITS = 14;
 constexpr unsigned BFS_HSLOTS = 1u << BFS_HBITS;           // 16384 slots, 64 KB
 constexpr unsigned BFS_EMPTY = 0xffffffffu;
+constexpr unsigned BFS_BU_MAX = BFS_HSLOTS / 2;             // bottom-up levels sort <= 8192 64-bit keys in the table's memory
 // shared memory: table | start[1025] | a0[1024] | warp totals[2][32] | pad | bitmap
 constexpr unsigned BFS_FIXED_WORDS = BFS_HSLOTS + (BFS_THREADS + 1) + BFS_THREADS + 64 + 31;
 constexpr long long BFS_SMEM_MAX_BYTES = 227 * 1024;
@@ -77,7 +78,7 @@ template <bool VSMEM>
 __global__ void __launch_bounds__(BFS_THREADS, 1)
 bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__restrict__ adj, long long n_roots,
            const int *__restrict__ roots, uint32_t *__restrict__ tree_bits, long long tree_words, uint2 *__restrict__ qbuf,
-           unsigned *__restrict__ gbitmap, int tagbits) {
+           unsigned *__restrict__ posbuf, unsigned *__restrict__ gbitmap, int tagbits, unsigned avg_deg) {
     extern __shared__ __align__(16) unsigned bfs_smem[];
     unsigned *table = bfs_smem;
     unsigned *start = table + BFS_HSLOTS;                  // [1025] exclusive prefix of the window's degrees
@@ -90,6 +91,8 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
     // The random indptr reads are issued when a node is APPENDED (fire and forget behind the compaction scan), so the
     // frontier sweep itself reads the queue sequentially and one window ahead.
     uint2 *Q = qbuf + (size_t)blockIdx.x * (size_t)n_node;
+    unsigned *pos = posbuf + (size_t)blockIdx.x * (size_t)n_node;        // node -> queue position (bottom-up levels)
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(table);   // bottom-up levels reuse the table
     const unsigned *ip32 = reinterpret_cast<const unsigned *>(indptr);   // low words (nnz < 2^31, little endian)
     const int tid = threadIdx.x;
     const unsigned tagmask = (1u << tagbits) - 1u;
@@ -104,10 +107,80 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
         if (tid == 0) {
             V[root >> 5] = 1u << (root & 31);
             Q[0] = make_uint2(ip32[2 * (size_t)root], ip32[2 * (size_t)root + 2] - ip32[2 * (size_t)root]);
+            pos[root] = 0u;
         }
         __syncthreads();
         unsigned lo = 0, hi = 1, tail = 1, flip = 0;
+        unsigned deg_acc = 0;                               // degrees of the nodes I appended during this level
+        unsigned long long fe = 0;                          // adjacency entries of the current frontier (0: unknown / small)
         while (lo < hi) {                                   // one BFS level: queue entries [lo, hi)
+            // ---- direction: when almost everything is discovered, the frontier's adjacency (millions of entries, hardly
+            // any of them leading to a new node) is not swept; instead the few undiscovered nodes look for their father:
+            // the visited neighbour with the smallest queue position (every visited neighbour of an undiscovered node is
+            // on the current frontier), and the new nodes are appended sorted by (father's position, entry in the father's
+            // adjacency) -- exactly the order the sweep would have produced.
+            const unsigned undiscovered = (unsigned)n_node - tail;
+            if (undiscovered <= BFS_BU_MAX && fe > 4ull * ((unsigned long long)undiscovered * avg_deg + bm_words)) {
+                if (tid == 0) *s_win = 0u;
+                __syncthreads();
+                for (size_t wi = tid; wi < bm_words; wi += BFS_THREADS) {
+                    unsigned word = ~(VSMEM ? V[wi] : __ldcg(V + wi));
+                    if (wi == bm_words - 1 && (n_node & 31)) word &= (1u << (n_node & 31)) - 1u;
+                    while (word) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1u;
+                        const int w = (int)(wi * 32 + b);
+                        const unsigned a0 = ip32[2 * (size_t)w], a1 = ip32[2 * (size_t)w + 2];
+                        unsigned best = 0xffffffffu;
+                        for (unsigned e = a0; e < a1; ++e) {
+                            const int u = __ldg(adj + e);
+                            if (v_test<VSMEM>(V, u)) { const unsigned pu = __ldcg(pos + u); best = pu < best ? pu : best; }
+                        }
+                        if (best == 0xffffffffu) continue;   // not adjacent to the frontier (yet)
+                        const uint2 fq = __ldcg(Q + best);   // the father's adjacency entries
+                        unsigned ef = fq.x;
+                        while (ef < fq.x + fq.y && __ldg(adj + ef) != w) ++ef;
+                        keys[atomicAdd(s_win, 1u)] = ((unsigned long long)best << 32) | ef;
+                    }
+                }
+                __syncthreads();
+                const unsigned n_new = *s_win;
+                unsigned n2 = 32;
+                while (n2 < n_new) n2 <<= 1;
+                for (unsigned i = n_new + tid; i < n2; i += BFS_THREADS) keys[i] = ~0ull;
+                __syncthreads();
+                for (unsigned k = 2; k <= n2; k <<= 1) {     // bitonic sort, ascending
+                    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                        for (unsigned i = tid; i < n2; i += BFS_THREADS) {
+                            const unsigned p2 = i ^ j;
+                            if (p2 > i) {
+                                const unsigned long long x = keys[i], y = keys[p2];
+                                if ((x > y) == ((i & k) == 0)) { keys[i] = y; keys[p2] = x; }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                for (unsigned i = tid; i < n_new; i += BFS_THREADS) {
+                    const unsigned ef = (unsigned)(keys[i] & 0xffffffffull);
+                    const int w = __ldg(adj + ef);
+                    const unsigned qa = ip32[2 * (size_t)w], qb = ip32[2 * (size_t)w + 2];
+                    Q[tail + i] = make_uint2(qa, qb - qa);
+                    pos[w] = tail + i;
+                    deg_acc += qb - qa;
+                    atomicOr(V + (w >> 5), 1u << (w & 31));
+                    atomicOr(tb + (ef >> 5), 1u << (ef & 31));
+                }
+                __syncthreads();
+                for (unsigned sidx = tid; sidx < 2 * BFS_BU_MAX && sidx < BFS_HSLOTS; sidx += BFS_THREADS) table[sidx] = BFS_EMPTY;
+                tail += n_new;
+                unsigned tot2;
+                block_scan_incl(deg_acc, s_tot + 32 * (flip ^= 1u), tot2);
+                fe = tot2; deg_acc = 0;
+                __syncthreads();
+                lo = hi; hi = tail;
+                continue;
+            }
             unsigned pf_i = 0xffffffffu;                    // prefetched window (valid inside a level only)
             uint2 pf = make_uint2(0u, 0u);
             for (unsigned wbase = lo; wbase < hi; wbase += BFS_THREADS) {
@@ -239,6 +312,8 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
 #pragma unroll
                         for (int x = 0; x < BFS_EPT; ++x) {
                             if (!((wm >> x) & 1u)) continue;
+                            pos[w[x]] = off;
+                            deg_acc += qb[x] - qa[x];
                             Q[off++] = make_uint2(qa[x], qb[x] - qa[x]);
                             const unsigned wi = ee[x] >> 5;
                             if (wi != word) {
@@ -253,6 +328,11 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                     }
                     jlo += m;
                 }
+            }
+            {                                               // adjacency entries of the next frontier
+                unsigned tot2;
+                block_scan_incl(deg_acc, s_tot + 32 * (flip ^= 1u), tot2);
+                fe = tot2; deg_acc = 0;
             }
             __syncthreads();                                // the queue entries appended above are read next
             lo = hi; hi = tail;
@@ -293,7 +373,7 @@ extern "C" int gg_bfs_scratch_bytes(int64_t n_node, int64_t nnz, int64_t *bytes)
     GG_REQUIRE(bytes && n_node >= 0 && nnz >= 0, "bad arguments");
     const long long bm_bytes = (n_node + 31) / 32 * 4;
     const bool in_smem = bm_bytes <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
-    *bytes = (int64_t)gg::sm_count() * (8 * n_node + (in_smem ? 0 : bm_bytes)) + 16;
+    *bytes = (int64_t)gg::sm_count() * (12 * n_node + (in_smem ? 0 : bm_bytes)) + 16;
     return 0;
 }
 
@@ -306,7 +386,7 @@ extern "C" int gg_bfs_build(int64_t n_node, int64_t nnz, const int64_t *indptr, 
     if (n_roots == 0 || n_node == 0) return 0;
     const long long bm_bytes = (n_node + 31) / 32 * 4;
     const bool in_smem = bm_bytes <= gg::BFS_SMEM_BITMAP_MAX_BYTES;
-    const int64_t per_cta = 8 * n_node + (in_smem ? 0 : bm_bytes);
+    const int64_t per_cta = 12 * n_node + (in_smem ? 0 : bm_bytes);
     int64_t ctas = scratch_bytes / per_cta;
     if (ctas > gg::sm_count()) ctas = gg::sm_count();
     if (ctas > n_roots) ctas = n_roots;
@@ -314,17 +394,19 @@ extern "C" int gg_bfs_build(int64_t n_node, int64_t nnz, const int64_t *indptr, 
     const int tagbits = gg::bfs_tagbits(n_node);
     GG_REQUIRE(tagbits + 10 <= 31, "graph too large for the 32-bit proposal keys");
     uint2 *qbuf = (uint2 *)scratch;
-    unsigned *gbm = in_smem ? nullptr : (unsigned *)(qbuf + (size_t)ctas * (size_t)n_node);
+    unsigned *posbuf = (unsigned *)(qbuf + (size_t)ctas * (size_t)n_node);
+    unsigned *gbm = in_smem ? nullptr : posbuf + (size_t)ctas * (size_t)n_node;
+    const unsigned avg_deg = (unsigned)((nnz + n_node - 1) / n_node > 0 ? (nnz + n_node - 1) / n_node : 1);
     const size_t smem = 4 * (size_t)gg::BFS_FIXED_WORDS + (in_smem ? (size_t)bm_bytes : 0);
     cudaStream_t st = (cudaStream_t)stream;
     if (in_smem) {
         GG_CHECK(cudaFuncSetAttribute(gg::bfs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gg::bfs_kernel<true><<<(unsigned)ctas, gg::BFS_THREADS, smem, st>>>(
-            n_node, (const long long *)indptr, adj, n_roots, roots, tree_bits, tree_words, qbuf, gbm, tagbits);
+            n_node, (const long long *)indptr, adj, n_roots, roots, tree_bits, tree_words, qbuf, posbuf, gbm, tagbits, avg_deg);
     } else {
         GG_CHECK(cudaFuncSetAttribute(gg::bfs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gg::bfs_kernel<false><<<(unsigned)ctas, gg::BFS_THREADS, smem, st>>>(
-            n_node, (const long long *)indptr, adj, n_roots, roots, tree_bits, tree_words, qbuf, gbm, tagbits);
+            n_node, (const long long *)indptr, adj, n_roots, roots, tree_bits, tree_words, qbuf, posbuf, gbm, tagbits, avg_deg);
     }
     return gg::check_cuda(cudaGetLastError(), "bfs kernel launch");
 }

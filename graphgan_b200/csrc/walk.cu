@@ -112,7 +112,7 @@ __device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const 
 // Candidate list of `cur` in the tree of the root whose tree row is `tb` (graph_gan.py:250-259):
 // [father] + children in adjacency order, with scores all_score[cur, cand] (generator.py:21) -- cached hub
 // scores or the on-demand canonical dot -- and their max.  Warp-cooperative; results are warp-uniform.
-template <int CPL>
+template <int CPL, int U>
 __device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t *__restrict__ tb, int cur, int prev,
                                            bool inc_father, int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
                                            int &n_out, float &m_out, int *&ids_out, float *&sc_out,
@@ -126,7 +126,7 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t
     float m = -INFINITY;   // running max of the cached scores (lane local)
     const long long t_e = clock64();
     // (16 tiles in flight for hub adjacency was measured: the extra registers spill and the kernel gets slower)
-    enumerate_children<UNR>(d, tb, a0, a1, cached, ids, sc, lane, n, m);
+    enumerate_children<U>(d, tb, a0, a1, cached, ids, sc, lane, n, m);
     __syncwarp();
     const long long t_s = clock64();
     cyc[0] += (unsigned int)(t_s - t_e);
@@ -205,7 +205,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             if (d.for_d && step == 1) inc_father = false;
             if (!d.for_d && step == 1 && ((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u)) inc_father = false;
             int *ids; float *sc; float m;
-            build_list<CPL>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
+            build_list<CPL, UNR>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
             if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
 
             // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
@@ -312,12 +312,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) step1_cdf_k
         const int c = __ldg(d.adj + e);
         const bool inc_father = !d.for_d && !((d.d1_bits[e >> 5] >> (e & 31)) & 1u);   // graph_gan.py:258-259
         int n; float m; int *ids; float *sc;
-        build_list<CPL>(d, tb, c, root, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
+        build_list<CPL, UNR_S1>(d, tb, c, root, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
         if (lane == 0) d.s1_n[pos] = n;
         if (n == 0) continue;
         const long long o = __ldg(d.s1_ptr + pos);
         for (int i = lane; i < n; i += 32) d.s1_ids[o + i] = ids[i];
-        if (n > 1) cdf_store_raw(sc, n, m, d.s1_q + o, lane);
+        if (n > 1) cdf_store_raw<UNR_S1>(sc, n, m, d.s1_q + o, lane);
         __syncwarp();
     }
     if (lane == 0 && rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);

@@ -10,13 +10,16 @@ namespace gg {
 // bound, so the trade is occupancy (registers, shared memory per warp) against loads in flight per warp (unrolling)
 // and against instruction footprint (the hot path must stay near the 32 KB L1.5 instruction cache).
 #ifndef GG_SC_CAP
-#define GG_SC_CAP 2048
+#define GG_SC_CAP 1024
 #endif
 #ifndef GG_UNR
-#define GG_UNR 4
+#define GG_UNR 2
+#endif
+#ifndef GG_UNR_S1
+#define GG_UNR_S1 4
 #endif
 #ifndef GG_WALK_MIN_CTAS
-#define GG_WALK_MIN_CTAS 3
+#define GG_WALK_MIN_CTAS 4
 #endif
 constexpr int WARPS_PER_CTA = 8;
 constexpr int WALK_MIN_CTAS = GG_WALK_MIN_CTAS;   // CTAs per SM the walk kernels are compiled and launched for
@@ -24,7 +27,8 @@ constexpr int ID_CAP = 320;    // candidate ids per warp kept in shared memory (
 constexpr int SC_CAP = GG_SC_CAP;   // candidate scores per warp kept in shared memory
 constexpr int SMEM_CAP = ID_CAP;
 constexpr int WALK_SMEM_PER_WARP = SC_CAP * 4 + ID_CAP * 4;
-constexpr int UNR = GG_UNR;    // tiles of 32 candidates in flight per pass iteration
+constexpr int UNR = GG_UNR;    // tiles of 32 candidates in flight per pass iteration (walk kernel: short lists, many warps)
+constexpr int UNR_S1 = GG_UNR_S1;   // same, for the per-pass list builders (step1_cdf_kernel: long lists)
 
 // cur row in registers: lane (grp, g) holds float4 chunks g, g+8, ... (replicated over the 4 groups)
 template <int CPL>
@@ -260,9 +264,9 @@ __device__ __forceinline__ int choose_index(float *sc, int n, float m, double u,
 // normalised CDF q_i = cdf_i / total written out (the array numpy's choice would searchsorted)
 __device__ __forceinline__ void cdf_store(float *sc, int n, double *q_out, int lane) {
     const float m = list_max(sc, n, lane);
-    const float S = softmax_exp_sum(sc, n, m, lane);
+    const float S = softmax_exp_sum<UNR_S1>(sc, n, m, lane);
     double car[2];
-    const double total = cdf_total(sc, n, S, lane, car);
+    const double total = cdf_total<UNR_S1>(sc, n, S, lane, car);
     double carry = 0.0;
     for (int t0 = 0; t0 < n; t0 += 32) {
         const int i = t0 + lane;
@@ -275,20 +279,21 @@ __device__ __forceinline__ void cdf_store(float *sc, int n, double *q_out, int l
 
 // un-normalised CDF c_i = carry + scan(e/S)_i written out, the total after the n entries (c[n] = total).  One scan
 // pass: the division by the total is left to the search, which performs it only on the entries it probes.
+template <int U>
 __device__ __forceinline__ void cdf_store_raw(float *sc, int n, float m, double *c_out, int lane) {
-    const float S = softmax_exp_sum(sc, n, m, lane);
+    const float S = softmax_exp_sum<U>(sc, n, m, lane);
     double carry = 0.0;
-    for (int t0 = 0; t0 < n; t0 += 32 * UNR) {
-        double x[UNR];
+    for (int t0 = 0; t0 < n; t0 += 32 * U) {
+        double x[U];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int i = t0 + 32 * u + lane;
             x[u] = (i < n) ? (double)__fdiv_rn(sc[i], S) : 0.0;   // 0 / S == 0 for the padding lanes
         }
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) x[u] = warp_scan_ks(x[u], lane);
+        for (int u = 0; u < U; ++u) x[u] = warp_scan_ks(x[u], lane);
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (t0 + 32 * u >= n) break;               // warp-uniform
             const int i = t0 + 32 * u + lane;
             if (i < n) c_out[i] = __dadd_rn(carry, x[u]);

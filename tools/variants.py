@@ -14,11 +14,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    "base": [],
-    "occ4": ["GG_WALK_MIN_CTAS=4", "GG_SC_CAP=1024"],
-    "occ4_unr2": ["GG_WALK_MIN_CTAS=4", "GG_SC_CAP=1024", "GG_UNR=2"],
-    "unr2": ["GG_UNR=2"],
-    "occ5_unr2": ["GG_WALK_MIN_CTAS=5", "GG_SC_CAP=1024", "GG_UNR=2"],
+    "base": [],                                   # defaults of csrc/walk_common.cuh: 4 CTAs/SM, 1024 scores, UNR 2 / 4
+    "r1": ["GG_WALK_MIN_CTAS=3", "GG_SC_CAP=2048", "GG_UNR=4"],      # the round-1 configuration
+    "occ5": ["GG_WALK_MIN_CTAS=5"],
+    "unr1": ["GG_UNR=1"],
+    "s1unr8": ["GG_UNR_S1=8"],
 }
 
 
