@@ -53,6 +53,7 @@ def parse():
     p.add_argument("--file-order", action="store_true", help="start the walks in root order instead of hub-neighbourhoods first")
     p.add_argument("--no-depth1", dest="depth1", action="store_false",
                    help="disable the per-(root, depth-1 child) CDF reuse (csrc/walk.cu: step1_cdf_kernel)")
+    p.add_argument("--no-tma", action="store_true", help="enumerate hub lists with plain loads instead of cp.async.bulk staging (A/B)")
     p.add_argument("--verify", type=int, default=12, help="roots of the last timed pass re-derived with the C oracle (0 = off)")
     p.add_argument("--verify-seconds", type=float, default=45.0, help="time budget of --verify")
     p.add_argument("--g-steps", type=int, default=5, help="timed generator-mode passes (0 = skip)")
@@ -61,6 +62,8 @@ def parse():
     p.add_argument("--score-mode", default="lazy", choices=["lazy", "literal"],
                    help="--impl reference: 'literal' recomputes the whole N x N all_score per root exactly as graph_gan.py:238 does "
                         "(only feasible at C1); 'lazy' scores the candidates on demand (the only form that exists at N >= 1e5)")
+    p.add_argument("--transport", default="nccl", choices=["nccl", "p2p"],
+                   help="--phase update: gradient exchange by ncclAllGather or by peer-memory stores fused into the gradient kernel")
     p.add_argument("--adam-path", default="tma", choices=["tma", "ldg"],
                    help="K3 sweep: cp.async.bulk (TMA) pipeline or the per-thread-load kernel (A/B; sets GG_ADAM_PATH)")
     p.add_argument("--phase", default="sample", choices=["sample", "reward", "adam", "bfs", "update"],
@@ -440,7 +443,7 @@ def run_b200(args):
 
     hg, emb_h, roots, d = make_inputs(args, rank)
     dg = G.DeviceGraph(hg, dev)
-    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, depth1=args.depth1, hub_first=not args.file_order)
+    smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, depth1=args.depth1, hub_first=not args.file_order, tma=not args.no_tma)
     emb = S.pad_embedding(emb_h, dev)
     bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -801,7 +804,7 @@ def run_phase(args):
                                           "algorithmic_bytes_per_launch": alg, "note": "24 * N * ld bytes per step: read + write of E, m, v"}})
             else:
                 from graphgan_b200.parallel import DataParallelStep
-                dp = DataParallelStep(m) if world > 1 else None
+                dp = DataParallelStep(m, transport=args.transport) if world > 1 else None
                 def fn(s):
                     if dp is not None:
                         dp.step(i, j, lab)
@@ -814,7 +817,7 @@ def run_phase(args):
                              "unit": "steps/s", "ms_per_step": k_ms, "scaling": "strong",
                              "gpu_launches": (4 if world > 1 else 2) * args.steps,
                              "config": {"workload": "N=%d n_emb=%d (ld %d): one 64-pair d_updates step = pair-grad on this rank's slice -> "
-                                                    "%s -> merge -> dense Adam sweep" % (n, d, ld, "ncclAllGather of the compact gradients (C ABI: gg_dp_step)" if world > 1 else "no collective (1 GPU)"),
+                                                    "%s -> merge -> dense Adam sweep" % (n, d, ld, ("ncclAllGather of the compact gradients (C ABI: gg_dp_step)" if args.transport == "nccl" else "peer-memory stores from the gradient kernel + flag wait (C ABI: gg_dp_step, p2p)") if world > 1 else "no collective (1 GPU)"),
                                         "l2_policy": "inputs larger than L2 (E, m, v = %d MB)" % (3 * n * ld * 4 >> 20),
                                         "parallelism": "replicated parameters, batch rows split over %d GPU(s)" % world},
                              "collective": extra,

@@ -31,7 +31,7 @@ class WalkDesc(C.Structure):
         ("wsuml", C.c_void_p), ("paths", C.c_void_p), ("path_len", C.c_void_p), ("counters", C.c_void_p),
         ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64), ("work_counter", C.c_void_p),
         ("edge_score", C.c_void_p), ("root_q", C.c_void_p), ("rq_ptr", C.c_void_p),
-        ("hub_threshold", C.c_int32), ("reserved2", C.c_int32), ("walk_slot", C.c_void_p),
+        ("hub_threshold", C.c_int32), ("no_tma", C.c_int32), ("walk_slot", C.c_void_p),
         ("s1_nq", C.c_int64), ("s1_slot", C.c_void_p), ("s1_ptr", C.c_void_p), ("s1_cnt", C.c_void_p), ("s1_n", C.c_void_p),
         ("s1_q", C.c_void_p), ("s1_ids", C.c_void_p), ("first_idx", C.c_void_p), ("s1_order", C.c_void_p), ("walk_order", C.c_void_p),
     ]
@@ -61,6 +61,9 @@ SIGNATURES = {
     "gg_comm_init": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
     "gg_comm_destroy": (C.c_int, [_P]),
     "gg_comm_info": (C.c_int, [_P, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32), C.POINTER(C.c_uint64)]),
+    "gg_comm_p2p_export": (C.c_int, [_P, _I64, _P]),
+    "gg_comm_p2p_connect": (C.c_int, [_P, _P]),
+    "gg_comm_use_p2p": (C.c_int, [_P, _I32]),
     "gg_dp_step": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I32, _P, _P, _P, _P, _P,
                             _F, _F, _F, _F, _P]),
     "gg_dp_train_steps": (C.c_int, [_P, _I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I32,

@@ -69,8 +69,82 @@ int check_nccl(ncclResult_t r, const char *what) {
 struct Comm {
     ncclComm_t comm;
     int rank, world;
-    unsigned long long collectives;       // issued through this handle (diagnostic, read by gg_comm_info)
+    unsigned long long collectives;       // NCCL collectives issued through this handle (diagnostic, read by gg_comm_info)
+    // ---- optional peer-memory transport (gg_comm_p2p_*): every rank owns an exchange buffer that all peers map
+    // through CUDA IPC; the gradient kernel itself stores this rank's compact gradient into every peer's buffer
+    // over NVLink and raises a flag there, the merge kernel waits for the flags -- no collective call in the step
+    float *xbuf;                          // this rank's exchange buffer: [2][capacity] floats + [2][world] flags
+    long long capacity;                   // floats per parity half
+    float **peers_dev;                    // device array [world]: every rank's xbuf as mapped in THIS process
+    void *peer_map[64];                   // host copies (for cudaIpcCloseMemHandle)
+    unsigned step;                        // steps pushed so far (flag value of the next step = step + 1)
+    unsigned long long p2p_steps;
+    bool p2p;
 };
+
+// ---------------------------------------------------------------- fused gradient + exchange (peer memory)
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// K2 on this rank's slice of the mini-batch, then -- in the same kernel -- the exchange: the compact gradient (nf
+// floats) is stored into slot `rank` of EVERY rank's exchange buffer (peer stores over NVLink, 16 bytes per thread
+// per instruction) and, after a system-scope fence, a release store of the step number into that rank's flag word.
+__global__ void __launch_bounds__(GRAD_THREADS, 1)
+pair_grad_push_kernel(int mode, int B, int batch_total, const int *__restrict__ ni, const int *__restrict__ nj,
+                      const float *__restrict__ aux, const float *__restrict__ emb, const float *__restrict__ bias, int ld,
+                      float lambda, float *local_buf, int cap, int *row_slot, float *const *__restrict__ peers, int rank,
+                      int world, long long capacity, unsigned step_id) {
+    extern __shared__ int smem[];
+    const int tid = threadIdx.x;
+    const long long nf = (long long)cap * ld + 2ll * cap + 4;
+    float *rows_p = local_buf, *bias_p = local_buf + (size_t)cap * ld;
+    int *ids_p = reinterpret_cast<int *>(bias_p + cap), *nu_p = ids_p + cap;
+    if (B > 0) {
+        pair_grad_body<false>(smem, mode, B, batch_total, ni, nj, aux, emb, bias, ld, lambda, nu_p, ids_p, rows_p, bias_p, row_slot);
+    } else if (tid == 0) {
+        *nu_p = 0;
+    }
+    __threadfence();
+    __syncthreads();
+    const unsigned parity = step_id & 1u;
+    const int nu = *nu_p;                                      // only the used slots travel: rows [0, nu) + the tail
+    const long long tail0 = (long long)cap * ld;               // bias | ids | n_unique
+    const long long nrow4 = ((long long)nu * ld) >> 2, ntail4 = (nf - tail0) >> 2;
+    for (int r = 0; r < world; ++r) {
+        float *dst = peers[r] + (size_t)parity * (size_t)capacity + (size_t)rank * (size_t)nf;
+        const float4 *src4 = reinterpret_cast<const float4 *>(local_buf);
+        float4 *dst4 = reinterpret_cast<float4 *>(dst);
+        for (long long i = tid; i < nrow4; i += GRAD_THREADS) dst4[i] = src4[i];
+        for (long long i = tid; i < ntail4; i += GRAD_THREADS) dst4[(tail0 >> 2) + i] = src4[(tail0 >> 2) + i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+        unsigned *flags = reinterpret_cast<unsigned *>(peers[tid] + 2 * (size_t)capacity);
+        st_release_sys(flags + parity * world + rank, step_id);
+    }
+}
+
+// waits until every rank's gradient of step `step_id` has landed in THIS rank's exchange buffer, then the rank-major merge
+__global__ void __launch_bounds__(MERGE_THREADS, 1)
+merge_wait_kernel(int world, int cap, int ld, const float *xbuf, long long capacity, unsigned step_id, int *__restrict__ n_unique,
+                  int *__restrict__ uniq_ids, float *__restrict__ grad_rows, float *__restrict__ grad_bias,
+                  int *__restrict__ row_slot) {
+    extern __shared__ int smem[];
+    const unsigned parity = step_id & 1u;
+    if ((int)threadIdx.x < world) {
+        const unsigned *flag = reinterpret_cast<const unsigned *>(xbuf + 2 * (size_t)capacity) + parity * world + threadIdx.x;
+        while (ld_acquire_sys(flag) != step_id) __nanosleep(20);
+    }
+    __syncthreads();
+    grad_merge_body(smem, world, cap, ld, xbuf + (size_t)parity * (size_t)capacity, n_unique, uniq_ids, grad_rows, grad_bias, row_slot);
+}
 
 }  // namespace
 }  // namespace gg
@@ -97,7 +171,10 @@ extern "C" int gg_comm_init(const void *id128, int32_t rank, int32_t world, void
     GG_REQUIRE(n.ok, "libnccl.so.2 not found (dlopen)");
     gg::ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    gg::Comm *c = new gg::Comm{nullptr, rank, world, 0ull};
+    gg::Comm *c = new gg::Comm();
+    c->comm = nullptr; c->rank = rank; c->world = world; c->collectives = 0ull;
+    c->xbuf = nullptr; c->capacity = 0; c->peers_dev = nullptr; c->step = 0u; c->p2p_steps = 0ull; c->p2p = false;
+    for (int i = 0; i < 64; ++i) c->peer_map[i] = nullptr;
     int rc = gg::check_nccl(n.CommInitRank(&c->comm, world, id, rank), "ncclCommInitRank");
     if (rc) { delete c; return rc; }
     *comm_out = c;
@@ -107,7 +184,11 @@ extern "C" int gg_comm_init(const void *id128, int32_t rank, int32_t world, void
 extern "C" int gg_comm_destroy(void *comm) {
     if (!comm) return 0;
     gg::Comm *c = (gg::Comm *)comm;
-    int rc = gg::check_nccl(gg::nccl().CommDestroy(c->comm), "ncclCommDestroy");
+    for (int r = 0; r < c->world && r < 64; ++r)
+        if (c->peer_map[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_map[r]);
+    if (c->peers_dev) cudaFree(c->peers_dev);
+    if (c->xbuf) cudaFree(c->xbuf);
+    int rc = c->comm ? gg::check_nccl(gg::nccl().CommDestroy(c->comm), "ncclCommDestroy") : 0;
     delete c;
     return rc;
 }
@@ -117,12 +198,57 @@ extern "C" int gg_comm_info(void *comm, int32_t *rank, int32_t *world, int32_t *
     gg::Comm *c = (gg::Comm *)comm;
     if (rank) *rank = c->rank;
     if (world) *world = c->world;
-    if (collectives) *collectives = c->collectives;
+    if (collectives) *collectives = c->collectives + c->p2p_steps;
     if (nccl_version) {
         int v = 0;
         if (gg::nccl().GetVersion) gg::nccl().GetVersion(&v);
         *nccl_version = v;
     }
+    return 0;
+}
+
+extern "C" int gg_comm_p2p_export(void *comm, int64_t capacity_floats, void *handle64) {
+    GG_REQUIRE(comm && handle64 && capacity_floats > 0, "bad arguments");
+    gg::Comm *c = (gg::Comm *)comm;
+    GG_REQUIRE(c->world <= 64, "at most 64 ranks");
+    GG_REQUIRE(!c->xbuf, "exchange buffer already created");
+    const long long cap4 = (capacity_floats + 3) & ~3ll;
+    const size_t bytes = (size_t)(2 * cap4 + 2 * c->world + 4) * 4;
+    GG_CHECK(cudaMalloc((void **)&c->xbuf, bytes));
+    GG_CHECK(cudaMemset(c->xbuf, 0, bytes));
+    c->capacity = cap4;
+    cudaIpcMemHandle_t h;
+    GG_CHECK(cudaIpcGetMemHandle(&h, c->xbuf));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int gg_comm_p2p_connect(void *comm, const void *all_handles) {
+    GG_REQUIRE(comm && all_handles, "bad arguments");
+    gg::Comm *c = (gg::Comm *)comm;
+    GG_REQUIRE(c->xbuf, "gg_comm_p2p_export first");
+    float *host_ptrs[64];
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) { host_ptrs[r] = c->xbuf; c->peer_map[r] = c->xbuf; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)all_handles + 64 * (size_t)r, 64);
+        void *p = nullptr;
+        GG_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_map[r] = p;
+        host_ptrs[r] = (float *)p;
+    }
+    GG_CHECK(cudaMalloc((void **)&c->peers_dev, sizeof(float *) * (size_t)c->world));
+    GG_CHECK(cudaMemcpy(c->peers_dev, host_ptrs, sizeof(float *) * (size_t)c->world, cudaMemcpyHostToDevice));
+    c->p2p = true;
+    return 0;
+}
+
+extern "C" int gg_comm_use_p2p(void *comm, int32_t on) {
+    GG_REQUIRE(comm, "null communicator");
+    gg::Comm *c = (gg::Comm *)comm;
+    GG_REQUIRE(!on || c->peers_dev, "peer memory is not connected (gg_comm_p2p_export / gg_comm_p2p_connect)");
+    c->p2p = on != 0;
     return 0;
 }
 
@@ -147,6 +273,30 @@ extern "C" int gg_dp_step(void *comm, int32_t mode, int32_t n_pairs, const int32
     int lo, hi;
     block_range(n_pairs, c->rank, c->world, &lo, &hi);
     const int64_t nf = gg_grad_buf_floats(cap, ld);
+    if (c->p2p) {
+        // ---- peer-memory transport: gradient + exchange in ONE kernel (stores into every peer's buffer over NVLink),
+        // then the merge kernel waits for all ranks' flags of this step
+        GG_REQUIRE((int64_t)c->world * nf <= c->capacity, "exchange buffer too small for this cap / ld");
+        GG_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (discriminator) or 1 (generator)");
+        GG_REQUIRE(ld == 32 || ld == 64 || ld == 128 || ld == 256, "ld must be 32, 64, 128 or 256 (row stride in floats)");
+        const unsigned step_id = ++c->step;
+        const int B = hi - lo;
+        const size_t smem_g = gg::pair_grad_smem_bytes(B > 0 ? B : 1);
+        gg::pair_grad_push_kernel<<<1, gg::GRAD_THREADS, smem_g, st>>>(mode, B, n_pairs, node_id + lo, node_neighbor_id + lo, aux + lo, emb,
+                                                                      bias, ld, lambda, local_buf, cap, row_slot, c->peers_dev, c->rank,
+                                                                      c->world, c->capacity, step_id);
+        GG_CHECK(cudaGetLastError());
+        const size_t smem_m = (size_t)c->world * cap * 2 * 4;
+        GG_REQUIRE(smem_m <= 200 * 1024, "merge exceeds shared memory");
+        if (smem_m > 48 * 1024)
+            GG_CHECK(cudaFuncSetAttribute(gg::merge_wait_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+        gg::merge_wait_kernel<<<1, gg::MERGE_THREADS, smem_m, st>>>(c->world, cap, ld, c->xbuf, c->capacity, step_id, n_unique, uniq_ids,
+                                                                   grad_rows, grad_bias, row_slot);
+        GG_CHECK(cudaGetLastError());
+        c->p2p_steps += 1;
+        return gg_adam_apply(n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, n_unique, uniq_ids, grad_rows, grad_bias, row_slot,
+                             lr_t, beta1, beta2, eps, stream);
+    }
     float *rows_p = local_buf, *bias_p = local_buf + (size_t)cap * ld;
     int32_t *ids_p = (int32_t *)(bias_p + cap), *nu_p = ids_p + cap;
     if (hi > lo) {      // K2 on this rank's slice; the generator loss is a mean over the WHOLE batch (batch_total)

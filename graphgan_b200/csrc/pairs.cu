@@ -74,80 +74,7 @@ grad_merge_kernel(int world, int cap, int ld, const float *__restrict__ gathered
                   int *__restrict__ uniq_ids, float *__restrict__ grad_rows, float *__restrict__ grad_bias,
                   int *__restrict__ row_slot) {
     extern __shared__ int smem[];
-    const int E = world * cap;
-    int *ids = smem;          // [E] row id or -1
-    int *slot = ids + E;      // [E]
-    __shared__ int s_warp[32];
-    __shared__ int s_total;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const size_t stride = (size_t)cap * ld + 2 * (size_t)cap + 4;   // == gg_grad_buf_floats
-    for (int t = tid; t < E; t += MERGE_THREADS) {
-        const int r = t / cap, sidx = t % cap;
-        const float *buf = gathered + (size_t)r * stride;
-        const int nu = __float_as_int(buf[(size_t)cap * ld + 2 * (size_t)cap]);
-        const int id = (sidx < nu) ? __float_as_int(buf[(size_t)cap * ld + cap + sidx]) : -1;
-        ids[t] = id;
-        if (id >= 0) row_slot[id] = -1;   // forget the slots of the local (pre-merge) gradient
-    }
-    __syncthreads();
-    int base_total = 0;
-    for (int t0 = 0; t0 < E; t0 += MERGE_THREADS) {
-        const int t = t0 + tid;
-        int is_first = 0, first_t = t;
-        if (t < E && ids[t] >= 0) {
-            const int id = ids[t];
-            int f = t;
-            for (int q = 0; q < t; ++q) if (ids[q] == id) { f = q; break; }
-            first_t = f; is_first = (f == t);
-        }
-        int x = is_first;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int y = __shfl_up_sync(FULL, x, off);
-            if (lane >= off) x += y;
-        }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            int v = s_warp[lane];
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int y = __shfl_up_sync(FULL, v, off);
-                if (lane >= off) v += y;
-            }
-            s_warp[lane] = v;
-        }
-        __syncthreads();
-        const int excl = base_total + (wid ? s_warp[wid - 1] : 0) + x - is_first;
-        if (t < E) slot[t] = (ids[t] < 0) ? -(E + 1) : (is_first ? excl : -1 - first_t);
-        if (t < E && is_first) { uniq_ids[excl] = ids[t]; row_slot[ids[t]] = excl; }
-        base_total += s_warp[31];
-        __syncthreads();
-    }
-    if (tid == 0) { s_total = base_total; *n_unique = base_total; }
-    __syncthreads();
-    for (int t = tid; t < E; t += MERGE_THREADS)
-        if (slot[t] < 0 && slot[t] != -(E + 1)) slot[t] = slot[-1 - slot[t]];
-    __syncthreads();
-    const int U = s_total;
-    for (int u = wid; u < U; u += MERGE_THREADS / 32) {
-        for (int c = 4 * lane; c < ld; c += 128) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int t = 0; t < E; ++t) {
-                if (slot[t] != u) continue;
-                const float4 o = *reinterpret_cast<const float4 *>(gathered + (size_t)(t / cap) * stride + (size_t)(t % cap) * ld + c);
-                acc.x = __fadd_rn(acc.x, o.x); acc.y = __fadd_rn(acc.y, o.y);
-                acc.z = __fadd_rn(acc.z, o.z); acc.w = __fadd_rn(acc.w, o.w);
-            }
-            *reinterpret_cast<float4 *>(grad_rows + (size_t)u * ld + c) = acc;
-        }
-        if (lane == 0) {
-            float gb = 0.0f;
-            for (int t = 0; t < E; ++t)
-                if (slot[t] == u) gb = __fadd_rn(gb, gathered[(size_t)(t / cap) * stride + (size_t)cap * ld + (t % cap)]);
-            grad_bias[u] = gb;
-        }
-    }
+    grad_merge_body(smem, world, cap, ld, gathered, n_unique, uniq_ids, grad_rows, grad_bias, row_slot);
 }
 
 // ---------------------------------------------------------------- window pairs (graph_gan.py:272-291)

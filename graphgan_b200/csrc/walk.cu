@@ -40,7 +40,8 @@ struct Rng {
 // bitmap words (1024 entries); only words with a set bit touch adj[] / edge_score[], U of them in flight.
 template <int U>
 __device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const uint32_t *__restrict__ tb, long long a0,
-                                                   long long a1, bool cached, int *ids, float *sc, int lane, int &n, float &m) {
+                                                   long long a1, bool cached, int *ids, float *sc, int lane, int &n, float &m,
+                                                   Stage &stg) {
     if (a1 <= a0) return;
     const unsigned lt = (1u << lane) - 1u;
     if (a1 - a0 <= 64) {
@@ -68,6 +69,45 @@ __device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const 
         return;
     }
     const long long wfirst = a0 >> 5, wlast = (a1 - 1) >> 5;
+    if (cached && stg.on && (a1 - a0 + 1) > SC_CAP) {
+        // ---- hub list, TMA staged: the list is longer than the warp's shared score buffer, so its scores go to the
+        // global scratch and the buffer is idle: each 512-entry block of adj[] and edge_score[] (contiguous, 128-B
+        // aligned) is brought in by ONE elected lane with two cp.async.bulk copies completing on the warp's mbarrier --
+        // one round trip per 512 entries instead of one per 128 -- while the lanes fetch the block's 16 bitmap words.
+        int *s_adj = reinterpret_cast<int *>(stg.buf);
+        float *s_cs = stg.buf + STAGE_ENTRIES;
+        const long long a1r = (a1 + 3) & ~3ll;                      // copy sizes are multiples of 16 bytes (arrays are padded)
+        for (long long eb = wfirst << 5; eb < a1; eb += STAGE_ENTRIES) {
+            const unsigned bytes = (unsigned)(((eb + STAGE_ENTRIES < a1r) ? (long long)STAGE_ENTRIES : (a1r - eb)) * 4);
+            if (lane == 0) {
+                mbar_expect_tx(stg.bar, 2 * bytes);
+                bulk_g2s(s_adj, d.adj + eb, bytes, stg.bar);
+                bulk_g2s(s_cs, d.edge_score + eb, bytes, stg.bar);
+            }
+            const long long wi = (eb >> 5) + lane;
+            unsigned word = (lane < STAGE_ENTRIES / 32 && wi <= wlast) ? __ldg(tb + wi) : 0u;
+            if (wi == wfirst) word &= 0xffffffffu << (a0 & 31);
+            if (wi == wlast && (a1 & 31)) word &= (1u << (a1 & 31)) - 1u;
+            unsigned nz = __ballot_sync(FULL, word != 0u);
+            mbar_wait(stg.bar, stg.phase);
+            stg.phase ^= 1u;
+            while (nz) {
+                const int j = __ffs(nz) - 1;
+                nz &= nz - 1u;
+                const unsigned wv = __shfl_sync(FULL, word, j);
+                if ((wv >> lane) & 1u) {
+                    const int pos = n + __popc(wv & lt);
+                    const float cs = s_cs[32 * j + lane];
+                    ids[pos] = s_adj[32 * j + lane];
+                    sc[pos] = cs;
+                    m = fmaxf(m, cs);
+                }
+                n += __popc(wv);
+            }
+            __syncwarp();                                           // every lane is done with the block before it is overwritten
+        }
+        return;
+    }
     for (long long wb = wfirst; wb <= wlast; wb += 32) {
         const long long wi = wb + lane;
         unsigned word = (wi <= wlast) ? __ldg(tb + wi) : 0u;
@@ -116,7 +156,7 @@ template <int CPL, int U>
 __device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t *__restrict__ tb, int cur, int prev,
                                            bool inc_father, int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
                                            int &n_out, float &m_out, int *&ids_out, float *&sc_out,
-                                           unsigned long long &rows_gathered, unsigned int (&cyc)[7]) {
+                                           unsigned long long &rows_gathered, unsigned int (&cyc)[7], Stage &stg) {
     const long long a0 = d.indptr[cur], a1 = d.indptr[cur + 1];
     const bool cached = d.edge_score && (a1 - a0) >= d.hub_threshold;  // scores precomputed per pass
     int *ids = (a1 - a0 + 1) <= ID_CAP ? s_ids : g_ids;
@@ -126,7 +166,7 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t
     float m = -INFINITY;   // running max of the cached scores (lane local)
     const long long t_e = clock64();
     // (16 tiles in flight for hub adjacency was measured: the extra registers spill and the kernel gets slower)
-    enumerate_children<U>(d, tb, a0, a1, cached, ids, sc, lane, n, m);
+    enumerate_children<U>(d, tb, a0, a1, cached, ids, sc, lane, n, m, stg);
     __syncwarp();
     const long long t_s = clock64();
     cyc[0] += (unsigned int)(t_s - t_e);
@@ -159,7 +199,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
                                         int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
                                         unsigned long long &raw_steps, unsigned long long &raw_suml,
                                         unsigned long long &overflow, unsigned long long &rows_gathered,
-                                        unsigned int (&cyc)[7]) {
+                                        unsigned int (&cyc)[7], Stage &stg) {
     const int root = d.roots[slot];
     const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
     int cur = root, prev = -1, step = 0, fedge = -1, plen = 0;
@@ -205,7 +245,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             if (d.for_d && step == 1) inc_father = false;
             if (!d.for_d && step == 1 && ((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u)) inc_father = false;
             int *ids; float *sc; float m;
-            build_list<CPL, UNR>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
+            build_list<CPL, UNR>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
             if (n == 0) { status = GG_VOID; break; }  // graph_gan.py:252-257
 
             // ---- softmax + inverse CDF (utils.py:131-133, np.random.choice at graph_gan.py:262)
@@ -274,6 +314,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) step1_cdf_k
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
     int *s_ids = reinterpret_cast<int *>(s_sc + SC_CAP);
+    Stage stg;
+    stg.buf = s_sc;
+    stg.bar = reinterpret_cast<unsigned long long *>(s_ids + ID_CAP);
+    stg.phase = 0u;
+    stg.on = !d.no_tma && d.edge_score != nullptr;
+    if (stg.on) {
+        if (lane == 0) {
+            mbar_init(stg.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
     const long long nwarps = (long long)gridDim.x * WARPS_PER_CTA;
     int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
@@ -312,7 +364,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) step1_cdf_k
         const int c = __ldg(d.adj + e);
         const bool inc_father = !d.for_d && !((d.d1_bits[e >> 5] >> (e & 31)) & 1u);   // graph_gan.py:258-259
         int n; float m; int *ids; float *sc;
-        build_list<CPL, UNR_S1>(d, tb, c, root, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc);
+        build_list<CPL, UNR_S1>(d, tb, c, root, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
         if (lane == 0) d.s1_n[pos] = n;
         if (n == 0) continue;
         const long long o = __ldg(d.s1_ptr + pos);
@@ -330,6 +382,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) walk_kernel
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
     int *s_ids = reinterpret_cast<int *>(s_sc + SC_CAP);
+    Stage stg;
+    stg.buf = s_sc;
+    stg.bar = reinterpret_cast<unsigned long long *>(s_ids + ID_CAP);
+    stg.phase = 0u;
+    stg.on = !d.no_tma && d.edge_score != nullptr;
+    if (stg.on) {
+        if (lane == 0) {
+            mbar_init(stg.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
     int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
     float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
@@ -371,7 +435,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) walk_kernel
             }
         }
         walk_one<CPL>(d, rng, slot, k, w, s_ids, s_sc, g_ids, g_sc, lane, raw_steps, raw_suml, overflow, rows_gathered,
-                      cyc);
+                      cyc, stg);
     }
     if (lane == 0) {
 #pragma unroll
@@ -399,6 +463,8 @@ __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__
     rng.stream = d.stream; rng.n_stream = d.n_stream; rng.cursor = 0; rng.exhausted = 0;
     unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
     unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
+    Stage stg;                                              // the replay kernel uses plain loads
+    stg.buf = s_sc; stg.bar = nullptr; stg.phase = 0u; stg.on = false;
     for (long long slot = 0; slot < d.n_roots && !rng.exhausted; ++slot) {
         const long long w0 = d.walk_ptr[slot], w1 = d.walk_ptr[slot + 1];
         const double ur = rng.draw(0, 0, 0);
@@ -414,7 +480,7 @@ __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__
                 continue;
             }
             const int st = walk_one<CPL>(d, rng, (int)slot, (uint32_t)(w - w0), w, s_ids, s_sc, g_ids, g_sc, lane,
-                                         raw_steps, raw_suml, overflow, rows_gathered, cyc);
+                                         raw_steps, raw_suml, overflow, rows_gathered, cyc, stg);
             if (st != GG_DONE) dead = true;
         }
     }

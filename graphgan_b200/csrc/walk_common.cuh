@@ -16,7 +16,7 @@ namespace gg {
 #define GG_UNR 2
 #endif
 #ifndef GG_UNR_S1
-#define GG_UNR_S1 4
+#define GG_UNR_S1 8
 #endif
 #ifndef GG_WALK_MIN_CTAS
 #define GG_WALK_MIN_CTAS 4
@@ -26,7 +26,18 @@ constexpr int WALK_MIN_CTAS = GG_WALK_MIN_CTAS;   // CTAs per SM the walk kernel
 constexpr int ID_CAP = 320;    // candidate ids per warp kept in shared memory (longer lists: global scratch)
 constexpr int SC_CAP = GG_SC_CAP;   // candidate scores per warp kept in shared memory
 constexpr int SMEM_CAP = ID_CAP;
-constexpr int WALK_SMEM_PER_WARP = SC_CAP * 4 + ID_CAP * 4;
+constexpr int WALK_SMEM_PER_WARP = SC_CAP * 4 + ID_CAP * 4 + 16;   // + the warp's mbarrier (TMA staging of hub lists)
+constexpr int STAGE_ENTRIES = 512;  // adjacency entries per bulk-copy block: 2 KB of ids + 2 KB of cached scores
+static_assert(2 * STAGE_ENTRIES * 4 <= SC_CAP * 4, "the staging area is the warp's (idle) score buffer");
+
+// Per-warp TMA staging state: `buf` = the warp's shared score buffer (free whenever a list is too long for it), `bar` =
+// the warp's mbarrier, `phase` = its parity.  on = false: plain loads (stream-replay kernel, or desc.no_tma).
+struct Stage {
+    float *buf;
+    unsigned long long *bar;
+    unsigned phase;
+    bool on;
+};
 constexpr int UNR = GG_UNR;    // tiles of 32 candidates in flight per pass iteration (walk kernel: short lists, many warps)
 constexpr int UNR_S1 = GG_UNR_S1;   // same, for the per-pass list builders (step1_cdf_kernel: long lists)
 

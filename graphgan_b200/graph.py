@@ -100,7 +100,8 @@ class DeviceGraph:
         self.n_node = host.n_node
         self.max_deg = host.max_deg
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
-        self.indptr, self.adj = t(host.indptr), t(host.adj)
+        # adj (and edge_score below) carry 4 padding entries: the TMA staging of hub lists copies whole 16-byte units
+        self.indptr, self.adj = t(host.indptr), t(np.concatenate([host.adj, np.zeros(4, np.int32)]))[:host.adj.shape[0]]
         same = host.raw_adj.shape == host.adj.shape and np.array_equal(host.raw_adj, host.adj)
         self.raw_indptr = self.indptr if same else t(host.raw_indptr)
         self.raw_adj = self.adj if same else t(host.raw_adj)
@@ -124,7 +125,7 @@ class DeviceGraph:
             self._hub = (torch.from_numpy(node).to(self.device), torch.from_numpy(begin).to(self.device),
                          int(node.shape[0]), int(deg[hubs].sum()))
             if not hasattr(self, "edge_score"):
-                self.edge_score = torch.empty(max(self.host.adj.shape[0], 1), dtype=torch.float32, device=self.device)
+                self.edge_score = torch.empty(self.host.adj.shape[0] + 4, dtype=torch.float32, device=self.device)[:max(self.host.adj.shape[0], 1)]
         return self._hub
 
     def reset_tree_mutations(self):

@@ -73,14 +73,32 @@ def create_comm(group=None):
     return handle
 
 
+def connect_peer_memory(comm, capacity_floats, group=None):
+    """Peer-memory transport of the data-parallel step (csrc/comm.cu): every rank creates its exchange buffer, the 64-byte
+    CUDA IPC handles are all-gathered with torch.distributed, every rank maps its peers' buffers (NVLink P2P)."""
+    import torch
+    import torch.distributed as dist
+    lib = _cabi.lib()
+    world = dist.get_world_size(group)
+    buf = C.create_string_buffer(64)
+    _cabi.check(lib.gg_comm_p2p_export(comm, int(capacity_floats), buf), "gg_comm_p2p_export")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    raw = b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh)
+    _cabi.check(lib.gg_comm_p2p_connect(comm, C.create_string_buffer(raw, 64 * world)), "gg_comm_p2p_connect")
+
+
 class DataParallelStep:
     """Data-parallel replacement for PairModel.step / train_steps: same arguments (the WHOLE mini-batch, identical on
     every rank).  The step -- gradient of this rank's rows, ONE ncclAllGather of the compact gradients, rank-major merge,
     Adam sweep -- runs inside the C library on the caller's stream (gg_dp_step / gg_dp_train_steps)."""
 
     _comm = None        # one library-owned communicator per process
+    _p2p_capacity = 0   # floats of the peer-memory exchange buffer (0: not connected)
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, transport="nccl"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.model, self.group = torch, dist, model, group
@@ -90,6 +108,21 @@ class DataParallelStep:
             DataParallelStep._comm = create_comm(group)
         self.comm = DataParallelStep._comm
         self._cap = None
+        self.transport = None
+        self.use(transport)
+
+    def use(self, transport):
+        """"nccl": one ncclAllGather per step; "p2p": the gradient kernel itself stores into every peer's exchange buffer
+        over NVLink (CUDA IPC mapped) and the merge kernel waits on flags -- no collective call.  Same results bit for bit."""
+        assert transport in ("nccl", "p2p")
+        if transport == "p2p" and DataParallelStep._p2p_capacity == 0:
+            cap_floats = self.world * int(self.lib.gg_grad_buf_floats(2 * (-(-256 // self.world)), 256))   # batches up to 256 pairs, ld 256
+            connect_peer_memory(self.comm, cap_floats, self.group)
+            DataParallelStep._p2p_capacity = cap_floats
+        self.transport = transport
+
+    def _select(self):
+        _cabi.check(self.lib.gg_comm_use_p2p(self.comm, 1 if self.transport == "p2p" else 0), "gg_comm_use_p2p")
 
     def _buffers(self, cap):
         torch, m = self.torch, self.model
@@ -108,6 +141,7 @@ class DataParallelStep:
             return
         cap = 2 * (-(-B // self.world))
         local, gathered = self._buffers(cap)
+        self._select()
         f = lambda x: C.c_float(float(x))
         _cabi.check(self.lib.gg_dp_step(self.comm, m._step_mode, B, ptr(i), ptr(j), ptr(a), m.n_node, m.ld, ptr(m.emb), ptr(m.m_emb),
                                         ptr(m.v_emb), ptr(m.bias_t), ptr(m.m_bias), ptr(m.v_bias), f(m.lam), ptr(local), ptr(gathered),
@@ -126,6 +160,7 @@ class DataParallelStep:
             return
         cap = 2 * (-(-int(batch_size) // self.world))
         local, gathered = self._buffers(cap)
+        self._select()
         f = lambda x: C.c_float(float(x))
         b1p, b2p = f(m.beta1_power), f(m.beta2_power)
         _cabi.check(self.lib.gg_dp_train_steps(self.comm, m._step_mode, int(i.shape[0]), starts.ctypes.data_as(C.c_void_p),
@@ -142,4 +177,6 @@ class DataParallelStep:
         r, w, v, n = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_uint64(0)
         _cabi.check(self.lib.gg_comm_info(self.comm, C.byref(r), C.byref(w), C.byref(v), C.byref(n)), "gg_comm_info")
         return {"rank": r.value, "comm_nranks": w.value, "nccl_version": v.value, "collectives_issued": int(n.value),
-                "bytes_per_rank_per_step": 4 * int(getattr(self, "_nf", 0)), "kind": "ncclAllGather (fp32) inside gg_dp_step"}
+                "bytes_per_rank_per_step": 4 * int(getattr(self, "_nf", 0)), "transport": self.transport,
+                "kind": "ncclAllGather (fp32) inside gg_dp_step" if self.transport == "nccl" else
+                        "peer stores into every rank's exchange buffer from the gradient kernel + flag wait in the merge kernel (gg_dp_step, p2p)"}

@@ -162,7 +162,7 @@ class WalkPlan:
 
 
 class WalkSampler:
-    def __init__(self, graph, hub_threshold=128, depth1=True, hub_first=True):
+    def __init__(self, graph, hub_threshold=128, depth1=True, hub_first=True, tma=True):
         import torch
         self.torch = torch
         self.g = graph
@@ -174,6 +174,7 @@ class WalkSampler:
         # share its candidate list (5.5x fewer neighbour probes at step 1 on C3); the builder kernel pulls the pairs
         # from a queue, largest lists first (hub_first), because a 13.8k-entry hub list occupies one warp for ~0.5-1 ms
         self.depth1 = bool(depth1)
+        self.tma = bool(tma)                      # cp.async.bulk staging of hub lists (csrc/walk.cu); False = plain loads (A/B)
         self.hub_first = bool(hub_first)          # start order of the walks (WalkPlan.start_order); results do not depend on it
         nbytes = C.c_int64(0)
         _cabi.check(self.lib.gg_walk_scratch_bytes(self.max_cand, C.byref(nbytes)), "gg_walk_scratch_bytes")
@@ -219,6 +220,7 @@ class WalkSampler:
         d.seed, d.pass_tag, d.max_path = seed, pass_tag, plan.max_path
         d.stream, d.n_stream = (ptr(stream), int(stream.numel())) if stream is not None else (None, 0)
         d.update_ratio, d.max_cand, d.phase_mask = float(update_ratio), self.max_cand, int(phase_mask)
+        d.no_tma = 0 if self.tma else 1
         d.samples, d.status, d.first_edge, d.wsteps, d.wsuml = (ptr(plan.samples), ptr(plan.status), ptr(plan.first_edge),
                                                                  ptr(plan.wsteps), ptr(plan.wsuml))
         d.paths, d.path_len, d.counters = ptr(plan.paths), ptr(plan.path_len), ptr(plan.counters)

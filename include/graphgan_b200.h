@@ -106,7 +106,8 @@ typedef struct gg_walk_desc {
                                    NULL = compute the root step per walk */
     const int64_t *rq_ptr;      /* device [R+1] offsets into root_q (prefix of the roots' walk-CSR degrees) */
     int32_t hub_threshold;
-    int32_t reserved2;
+    int32_t no_tma;             /* 1 = enumerate hub lists with plain loads instead of cp.async.bulk staging (A/B measurement;
+                                   identical results) */
     const int32_t *walk_slot;   /* optional device [W]: root slot of every walk (saves a binary search per walk) */
     /* optional depth-1 reuse (GG_RNG_PHILOX, needs root_q + walk_slot): the walks of a root that pick the same
        depth-1 child share one candidate list.  gg_walk_sample first runs the root step of every walk and counts
@@ -227,6 +228,14 @@ int gg_comm_unique_id(void *id128);
 int gg_comm_init(const void *id128, int32_t rank, int32_t world, void **comm_out);
 int gg_comm_destroy(void *comm);
 int gg_comm_info(void *comm, int32_t *rank, int32_t *world, int32_t *nccl_version, uint64_t *collectives);
+/* Peer-memory transport for the same step (optional; NVLink P2P through CUDA IPC, one process per GPU): every rank
+ * creates an exchange buffer (gg_comm_p2p_export -> 64-byte cudaIpcMemHandle_t), the caller all-gathers the handles,
+ * gg_comm_p2p_connect maps the peers' buffers.  With it, gg_dp_step runs the gradient AND the exchange in one kernel
+ * (stores into every peer's buffer + a release flag) and the merge kernel waits on the flags: no collective call per step.
+ * capacity_floats >= world * gg_grad_buf_floats(cap, ld).  gg_comm_use_p2p switches between the two transports. */
+int gg_comm_p2p_export(void *comm, int64_t capacity_floats, void *handle64);
+int gg_comm_p2p_connect(void *comm, const void *all_handles);
+int gg_comm_use_p2p(void *comm, int32_t on);
 int gg_dp_step(void *comm, int32_t mode, int32_t n_pairs, const int32_t *node_id, const int32_t *node_neighbor_id,
                const float *aux, int64_t n_node, int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias,
                float *m_bias, float *v_bias, float lambda, float *local_buf, float *gathered_buf, int32_t cap,

@@ -110,6 +110,16 @@ def main(mode):
         assert ra.beta1_power == rb.beta1_power and ra.step_count == rb.step_count
         st = db.stats()
         assert st["comm_nranks"] == world and st["collectives_issued"] - before == len(starts)
+        # the peer-memory transport (gradient + exchange fused in one kernel, NVLink P2P stores) == the NCCL transport
+        rc = cls(n, e0, device=dev)
+        dc = parallel.DataParallelStep(rc, transport="p2p")
+        dc.train_steps(ii, jj, ax, starts, Bs)
+        for name in ("emb", "bias_t", "m_emb", "v_emb", "m_bias", "v_bias"):
+            assert torch.equal(getattr(ra, name), getattr(rc, name)), ("p2p", name)
+        for s0 in starts[:3]:
+            dc.step(ii[s0:s0 + 5], jj[s0:s0 + 5], ax[s0:s0 + 5])      # short batches: some ranks own no row
+            da.step(ii[s0:s0 + 5], jj[s0:s0 + 5], ax[s0:s0 + 5])
+        assert torch.equal(ra.emb, rc.emb)
     # (3) the re-hosted trainer under torch.distributed: sharded sampling + data-parallel updates
     from graphgan_b200 import config
     from graphgan_b200.graph_gan import GraphGAN

@@ -239,6 +239,13 @@ def test_giant_hub_lists_beyond_the_smem_score_buffer(hub, cuda_device):
         assert np.array_equal(out.samples.cpu().numpy(), ref.samples)
         assert np.array_equal(out.wsuml.cpu().numpy(), ref.wsuml)
         assert np.array_equal(dg.d1_bits.cpu().numpy().view(np.uint32), bits)
+        if hub and not for_d:   # cp.async.bulk staging of the hub's adjacency / cached scores vs plain loads: same bits
+            got = {k: getattr(out, k).clone() for k in ("samples", "status", "wsteps", "wsuml", "path_len")}
+            smp.tma = False
+            out2 = smp.run(emb, bias, trees, torch.as_tensor(sample_num).to(cuda_device), for_d, seed=5, pass_tag=tag, max_path=16)
+            smp.tma = True
+            for k, v in got.items():
+                assert torch.equal(getattr(out2, k), v), k
 
 
 def test_partition_invariance(cuda_device):
