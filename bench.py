@@ -64,7 +64,7 @@ def parse():
                         "(only feasible at C1); 'lazy' scores the candidates on demand (the only form that exists at N >= 1e5)")
     p.add_argument("--transport", default="nccl", choices=["nccl", "p2p"],
                    help="--phase update: gradient exchange by ncclAllGather or by peer-memory stores fused into the gradient kernel")
-    p.add_argument("--adam-path", default="tma", choices=["tma", "ldg"],
+    p.add_argument("--adam-path", default="ldg", choices=["ldg", "tma", "tma256x2", "tma512x3"],
                    help="K3 sweep: cp.async.bulk (TMA) pipeline or the per-thread-load kernel (A/B; sets GG_ADAM_PATH)")
     p.add_argument("--phase", default="sample", choices=["sample", "reward", "adam", "bfs", "update"],
                    help="what to time: the D-sampling pass (the BASELINE metric) or one of the other kernels of the path")
@@ -799,7 +799,7 @@ def run_phase(args):
                              "ms_per_step": k_ms, "scaling": "weak", "gpu_launches": args.steps,
                              "config": {"workload": "N=%d n_emb=%d (ld %d): one dense Adam sweep over E, m, v per step" % (n, d, ld),
                                         "l2_policy": "inputs larger than L2 (E, m, v = %d MB)" % (3 * n * ld * 4 >> 20)},
-                             "roofline": {"bound": "hbm", "kernel": "gg::adam_tma_kernel" if args.adam_path == "tma" else "gg::adam_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak,
+                             "roofline": {"bound": "hbm", "kernel": "gg::adam_tma_kernel (%s)" % args.adam_path if args.adam_path != "ldg" else "gg::adam_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak,
                                           "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                                           "algorithmic_bytes_per_launch": alg, "note": "24 * N * ld bytes per step: read + write of E, m, v"}})
             else:

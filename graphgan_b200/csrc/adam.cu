@@ -36,10 +36,10 @@ __global__ void __launch_bounds__(256, 4) adam_kernel(long long n_node, int ld, 
 // IEEE div / sqrt chains of one tile overlap the transfers of the next ones with no registers spent on the pipeline.
 constexpr int ADAM_TILE = 2048;                   // floats per array per tile (8 KB): 64 / 32 / 16 / 8 rows
 constexpr int ADAM_STAGES = 4;
-constexpr int ADAM_THREADS = 256;
 constexpr size_t ADAM_TMA_SMEM = (size_t)ADAM_STAGES * 3 * ADAM_TILE * 4 + 64;
 
-__global__ void __launch_bounds__(ADAM_THREADS, 2)
+template <int ADAM_THREADS, int MINB>
+__global__ void __launch_bounds__(ADAM_THREADS, MINB)
 adam_tma_kernel(long long n_node, int ld, float *__restrict__ emb, float *__restrict__ m_emb, float *__restrict__ v_emb,
                 float *__restrict__ bias, float *__restrict__ m_bias, float *__restrict__ v_bias,
                 const float *__restrict__ grad_rows, const float *__restrict__ grad_bias, int *__restrict__ row_slot,
@@ -146,21 +146,33 @@ extern "C" int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_em
                              const float *grad_rows, const float *grad_bias, int32_t *row_slot, float lr_t, float beta1,
                              float beta2, float eps, void *stream) {
     (void)n_unique; (void)uniq_ids;
-    static int use_tma = -1;       // GG_ADAM_PATH=ldg selects the per-thread-load sweep (kept for the A/B measurement)
+    static int use_tma = -1;       // GG_ADAM_PATH=tma[...] selects the cp.async.bulk pipeline (A/B measurement)
     if (use_tma < 0) {
         const char *e = getenv("GG_ADAM_PATH");
-        use_tma = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
+        use_tma = 0;                          // default: the per-thread-load sweep (faster as measured)
+        if (e && strcmp(e, "tma") == 0) use_tma = 1;            // cp.async.bulk pipeline, 512 threads x 2 CTAs per SM
+        else if (e && strcmp(e, "tma256x2") == 0) use_tma = 2;
+        else if (e && strcmp(e, "tma512x3") == 0) use_tma = 3;
     }
     GG_REQUIRE(emb && m_emb && v_emb && bias && m_bias && v_bias && grad_rows && grad_bias && row_slot, "null pointer");
     GG_REQUIRE(ld == 32 || ld == 64 || ld == 128 || ld == 256, "ld must be 32, 64, 128 or 256 (row stride in floats)");
     if (n_node == 0) return 0;
     if (use_tma) {
         const long long n_tiles = (n_node * (long long)ld + gg::ADAM_TILE - 1) / gg::ADAM_TILE;
-        long long blocks = (long long)gg::sm_count() * 2;
-        if (blocks > n_tiles) blocks = n_tiles;
-        GG_CHECK(cudaFuncSetAttribute(gg::adam_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gg::ADAM_TMA_SMEM));
-        gg::adam_tma_kernel<<<(unsigned)blocks, gg::ADAM_THREADS, gg::ADAM_TMA_SMEM, (cudaStream_t)stream>>>(
-            n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, grad_rows, grad_bias, row_slot, lr_t, beta1, beta2, eps);
+        cudaStream_t st = (cudaStream_t)stream;
+#define GG_ADAM_TMA(NT, MINB)                                                                                                   \
+    do {                                                                                                                        \
+        long long blocks = (long long)gg::sm_count() * MINB;                                                                    \
+        if (blocks > n_tiles) blocks = n_tiles;                                                                                 \
+        GG_CHECK(cudaFuncSetAttribute(gg::adam_tma_kernel<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                      (int)gg::ADAM_TMA_SMEM));                                                                 \
+        gg::adam_tma_kernel<NT, MINB><<<(unsigned)blocks, NT, gg::ADAM_TMA_SMEM, st>>>(                                         \
+            n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, grad_rows, grad_bias, row_slot, lr_t, beta1, beta2, eps);      \
+    } while (0)
+        if (use_tma == 2) GG_ADAM_TMA(256, 2);
+        else if (use_tma == 3) GG_ADAM_TMA(512, 3);
+        else GG_ADAM_TMA(512, 2);
+#undef GG_ADAM_TMA
         return gg::check_cuda(cudaGetLastError(), "adam (TMA) kernel launch");
     }
     const int q = ld / 4;                                                       // float4 per row

@@ -297,32 +297,31 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                             anyw = (int)*s_win;
                         }
                         if (!anyw) continue;                // (uniform) nothing discovered by this slab: no compaction
-                        // ---- winners in entry order = FIFO order: append (entry range of the node) to the queue, set the
-                        // tree bits.  The indptr reads fly behind the scan's barrier.
-                        unsigned qa[BFS_EPT], qb[BFS_EPT];
-#pragma unroll
-                        for (int x = 0; x < BFS_EPT; ++x) {
-                            qa[x] = qb[x] = 0;
-                            if ((wm >> x) & 1u) { qa[x] = ip32[2 * (size_t)w[x]]; qb[x] = ip32[2 * (size_t)w[x] + 2]; }
-                        }
+                        // ---- winners in entry order = FIFO order.  They are sparse (a few per cent of the entries), so
+                        // they are first compacted into the (now idle, all-EMPTY) table as (head, entry) pairs at their FIFO
+                        // index, then handled one per thread: entry range of the node -> queue, queue position, tree bit.
                         unsigned ntot;
                         const unsigned cnt = (unsigned)__popc(wm);
-                        unsigned off = tail + block_scan_incl(cnt, s_tot + 32 * (flip ^= 1u), ntot) - cnt;
-                        unsigned word = 0xffffffffu, mask = 0;
+                        unsigned li = block_scan_incl(cnt, s_tot + 32 * (flip ^= 1u), ntot) - cnt;
+                        if (wm) {
 #pragma unroll
-                        for (int x = 0; x < BFS_EPT; ++x) {
-                            if (!((wm >> x) & 1u)) continue;
-                            pos[w[x]] = off;
-                            deg_acc += qb[x] - qa[x];
-                            Q[off++] = make_uint2(qa[x], qb[x] - qa[x]);
-                            const unsigned wi = ee[x] >> 5;
-                            if (wi != word) {
-                                if (mask) atomicOr(tb + word, mask);
-                                word = wi; mask = 0;
+                            for (int x = 0; x < BFS_EPT; ++x) {
+                                if (!((wm >> x) & 1u)) continue;
+                                table[2 * li] = (unsigned)w[x];
+                                table[2 * li + 1] = ee[x];
+                                ++li;
                             }
-                            mask |= 1u << (ee[x] & 31);
                         }
-                        if (mask) atomicOr(tb + word, mask);
+                        __syncthreads();
+                        for (unsigned i = tid; i < ntot; i += BFS_THREADS) {
+                            const unsigned wv = table[2 * i], e = table[2 * i + 1];
+                            table[2 * i] = BFS_EMPTY; table[2 * i + 1] = BFS_EMPTY;
+                            const unsigned qa = ip32[2 * (size_t)wv], qb = ip32[2 * (size_t)wv + 2];
+                            Q[tail + i] = make_uint2(qa, qb - qa);
+                            pos[wv] = tail + i;
+                            deg_acc += qb - qa;
+                            atomicOr(tb + (e >> 5), 1u << (e & 31));
+                        }
                         tail += ntot;
                         if (single && s0 + BFS_SLAB < Kend) __syncthreads();   // next slab of the same node: *s_win is not used
                     }

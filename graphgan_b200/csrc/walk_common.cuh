@@ -265,6 +265,16 @@ static __device__ __noinline__ int choose_index_long(float *sc, int n, float m, 
 }
 
 __device__ __forceinline__ int choose_index(float *sc, int n, float m, double u, int lane, double *tiles = nullptr) {
+    if (n <= 32) {
+        // one tile (the common case): S = 0 + T_0 = T_0, total = 0 + scan_31 = scan_31 and the carry of the draw is 0, so
+        // the canonical sequence collapses to ONE scan and ONE division per lane -- the same floats, bit for bit
+        const float e = (lane < n) ? exp_c(__fsub_rn(sc[lane], m)) : 0.0f;
+        const float S = warp_sum_butterfly(e);
+        const double x = warp_scan_ks((double)__fdiv_rn(e, S), lane);
+        const double total = __shfl_sync(FULL, x, 31);
+        const unsigned hit = __ballot_sync(FULL, (lane < n) && (__ddiv_rn(x, total) > u));
+        return hit ? __ffs(hit) - 1 : n - 1;
+    }
     if (n > SC_CAP) return choose_index_long(sc, n, m, u, lane, tiles);
     double car[2];
     const float S = softmax_exp_sum(sc, n, m, lane);

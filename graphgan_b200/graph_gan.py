@@ -301,8 +301,11 @@ class GraphGAN(object):
         ranks first, so the file holds the removals of every root."""
         torch = self.torch
         bits = self.device_graph.d1_bits.clone()
-        if self.dist:
-            self.dist.all_reduce(bits, op=self.dist.ReduceOp.BOR)
+        if self.dist:       # OR over the ranks (NCCL has no bitwise reduction: gather, then OR locally)
+            parts = [torch.empty_like(bits) for _ in range(self.world)]
+            self.dist.all_gather(parts, bits)
+            for p_ in parts:
+                bits |= p_
         if self.rank == 0:
             os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
             rs = self.shuffle_rng.get_state()
