@@ -64,7 +64,7 @@ def parse():
                         "(only feasible at C1); 'lazy' scores the candidates on demand (the only form that exists at N >= 1e5)")
     p.add_argument("--transport", default="nccl", choices=["nccl", "p2p"],
                    help="--phase update: gradient exchange by ncclAllGather or by peer-memory stores fused into the gradient kernel")
-    p.add_argument("--adam-path", default="ldg", choices=["ldg", "tma", "tma256x2", "tma512x3"],
+    p.add_argument("--adam-path", default="ldg", choices=["ldg", "tma", "tma256x2", "tma512x3", "ws16", "ws8"],
                    help="K3 sweep: cp.async.bulk (TMA) pipeline or the per-thread-load kernel (A/B; sets GG_ADAM_PATH)")
     p.add_argument("--phase", default="sample", choices=["sample", "reward", "adam", "bfs", "update"],
                    help="what to time: the D-sampling pass (the BASELINE metric) or one of the other kernels of the path")

@@ -68,6 +68,7 @@ SIGNATURES = {
                             _F, _F, _F, _F, _P]),
     "gg_dp_train_steps": (C.c_int, [_P, _I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I32,
                                    _P, _P, _P, _P, _P, _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),
+    "gg_set_adam_path": (C.c_int, [C.c_char_p]),
     "gg_adam_apply": (C.c_int, [_I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P]),
     "gg_train_steps": (C.c_int, [_I32, _I64, _P, _I64, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P,
                                 _F, _F, _F, _F, C.POINTER(C.c_float), C.POINTER(C.c_float), _P]),

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256, 4) adam_kernel(long long n_node, int ld, 
 // IEEE div / sqrt chains of one tile overlap the transfers of the next ones with no registers spent on the pipeline.
 constexpr int ADAM_TILE = 2048;                   // floats per array per tile (8 KB): 64 / 32 / 16 / 8 rows
 constexpr int ADAM_STAGES = 4;
-constexpr size_t ADAM_TMA_SMEM = (size_t)ADAM_STAGES * 3 * ADAM_TILE * 4 + 64;
+constexpr size_t ADAM_TMA_SMEM = (size_t)ADAM_STAGES * 3 * ADAM_TILE * 4 + 64;   // + the full / done mbarriers
 
 template <int ADAM_THREADS, int MINB>
 __global__ void __launch_bounds__(ADAM_THREADS, MINB)
@@ -138,22 +138,151 @@ adam_tma_kernel(long long n_node, int ld, float *__restrict__ emb, float *__rest
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA retires
 }
 
+// ---------------------------------------------------------------- warp-specialised TMA sweep
+// The CTA-wide barrier per tile of adam_tma_kernel serialises load -> compute -> store; here one PRODUCER warp owns the
+// copy engine (loads two tiles ahead, stores two tiles behind) and NCW consumer warps only ever wait on mbarriers:
+//   full[s]  (count 1 + tx bytes) : tile s has landed           producer -> consumers
+//   done[s]  (count NCW)          : every consumer warp is done   consumers -> producer (which then stores the tile)
+// so the div / sqrt chains of one tile overlap the transfers of the neighbouring ones without any thread idling at a
+// block barrier.  The row -> slot map is read by the consumers before they wait and cleared by the producer warp once
+// the tile is done (no consumer of that tile can still need it).
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int NCW, int MINB>
+__global__ void __launch_bounds__((NCW + 1) * 32, MINB)
+adam_ws_kernel(long long n_node, int ld, float *__restrict__ emb, float *__restrict__ m_emb, float *__restrict__ v_emb,
+               float *__restrict__ bias, float *__restrict__ m_bias, float *__restrict__ v_bias,
+               const float *__restrict__ grad_rows, const float *__restrict__ grad_bias, int *__restrict__ row_slot,
+               float lr_t, float b1, float b2, float eps) {
+    constexpr int NCT = NCW * 32, LAG = 2;
+    constexpr int PER = ADAM_TILE / (4 * NCT);                           // float4 per consumer thread per array per tile
+    static_assert(PER >= 1 && PER * 4 * NCT == ADAM_TILE, "tile must split evenly over the consumer threads");
+    extern __shared__ __align__(128) unsigned char adam_smem[];
+    float *buf = reinterpret_cast<float *>(adam_smem);                   // [STAGES][3][TILE]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(adam_smem + (size_t)ADAM_STAGES * 3 * ADAM_TILE * 4);
+    unsigned long long *done = full + ADAM_STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long total = n_node * (long long)ld;
+    const long long n_tiles = (total + ADAM_TILE - 1) / ADAM_TILE;
+    const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int s = 0; s < ADAM_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(done + s, NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (wid == NCW) {
+        // ---------------- producer warp
+        for (long long it = 0; it < my_tiles + LAG; ++it) {
+            if (it < my_tiles && lane == 0) {
+                if (it >= ADAM_STAGES) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(ADAM_STAGES - 1 - LAG) : "memory");
+                const int s = (int)(it % ADAM_STAGES);
+                const long long at = (blockIdx.x + it * gridDim.x) * (long long)ADAM_TILE;
+                const unsigned bytes = (unsigned)(((total - at) < ADAM_TILE ? (total - at) : ADAM_TILE) * 4);
+                float *sb = buf + (size_t)s * 3 * ADAM_TILE;
+                mbar_expect_tx(full + s, 3 * bytes);
+                bulk_g2s(sb, emb + at, bytes, full + s);
+                bulk_g2s(sb + ADAM_TILE, m_emb + at, bytes, full + s);
+                bulk_g2s(sb + 2 * ADAM_TILE, v_emb + at, bytes, full + s);
+            }
+            const long long j = it - LAG;
+            if (j >= 0) {
+                const int s = (int)(j % ADAM_STAGES);
+                mbar_wait(done + s, (unsigned)((j / ADAM_STAGES) & 1));
+                const long long at = (blockIdx.x + j * gridDim.x) * (long long)ADAM_TILE;
+                const int nfl = (int)((total - at) < ADAM_TILE ? (total - at) : ADAM_TILE);
+                const long long row0 = at / ld;
+                for (int r = lane; r < nfl / ld; r += 32)            // the tile's gradient slots are consumed: clear them
+                    if (row_slot[row0 + r] >= 0) row_slot[row0 + r] = -1;
+                if (lane == 0) {
+                    float *sb = buf + (size_t)s * 3 * ADAM_TILE;
+                    bulk_s2g(emb + at, sb, (unsigned)nfl * 4);
+                    bulk_s2g(m_emb + at, sb + ADAM_TILE, (unsigned)nfl * 4);
+                    bulk_s2g(v_emb + at, sb + 2 * ADAM_TILE, (unsigned)nfl * 4);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+    // ---------------- consumer warps
+    const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+    for (long long k = 0; k < my_tiles; ++k) {
+        const int s = (int)(k % ADAM_STAGES);
+        const long long at = (blockIdx.x + k * gridDim.x) * (long long)ADAM_TILE;
+        const int nfl = (int)((total - at) < ADAM_TILE ? (total - at) : ADAM_TILE);
+        const long long row0 = at / ld;
+        float *sx = buf + (size_t)s * 3 * ADAM_TILE, *sm = sx + ADAM_TILE, *sv = sx + 2 * ADAM_TILE;
+        int slot[PER];
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int e = 4 * (tid + NCT * p);
+            slot[p] = (e < nfl) ? row_slot[row0 + e / ld] : -1;
+        }
+        mbar_wait(full + s, (unsigned)((k / ADAM_STAGES) & 1));
+#define GG_ADAM_E(f)                                                                                  \
+    m4.f = __fadd_rn(__fmul_rn(m4.f, b1), __fmul_rn(omb1, g.f));                                      \
+    v4.f = __fadd_rn(__fmul_rn(v4.f, b2), __fmul_rn(__fmul_rn(g.f, g.f), omb2));                      \
+    x4.f = __fsub_rn(x4.f, __fdiv_rn(__fmul_rn(lr_t, m4.f), __fadd_rn(__fsqrt_rn(v4.f), eps)));
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int e = 4 * (tid + NCT * p);
+            if (e >= nfl) continue;
+            const int r = e / ld, c = e - r * ld;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (slot[p] >= 0) g = *reinterpret_cast<const float4 *>(grad_rows + (size_t)slot[p] * ld + c);
+            float4 x4 = *reinterpret_cast<float4 *>(sx + e), m4 = *reinterpret_cast<float4 *>(sm + e),
+                   v4 = *reinterpret_cast<float4 *>(sv + e);
+            GG_ADAM_E(x) GG_ADAM_E(y) GG_ADAM_E(z) GG_ADAM_E(w)
+            *reinterpret_cast<float4 *>(sx + e) = x4;
+            *reinterpret_cast<float4 *>(sm + e) = m4;
+            *reinterpret_cast<float4 *>(sv + e) = v4;
+            if (c == 0) {                         // this thread owns the row's bias
+                const long long row = row0 + r;
+                const float gb = slot[p] >= 0 ? grad_bias[slot[p]] : 0.0f;
+                const float mm = __fadd_rn(__fmul_rn(m_bias[row], b1), __fmul_rn(omb1, gb));
+                const float vv = __fadd_rn(__fmul_rn(v_bias[row], b2), __fmul_rn(__fmul_rn(gb, gb), omb2));
+                m_bias[row] = mm; v_bias[row] = vv;
+                bias[row] = __fsub_rn(bias[row], __fdiv_rn(__fmul_rn(lr_t, mm), __fadd_rn(__fsqrt_rn(vv), eps)));
+            }
+        }
+#undef GG_ADAM_E
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // my shared-memory writes -> visible to the copy engine
+        __syncwarp();
+        if (lane == 0) mbar_arrive(done + s);
+    }
+}
+
+// which sweep gg_adam_apply launches: 0 = per-thread loads (default: fastest measured), 1..3 = CTA-barrier TMA pipeline
+// (512x2, 256x2, 512x3 threads x CTAs per SM), 4 / 5 = warp-specialised TMA pipeline with 16 / 8 consumer warps
+int g_adam_path = -1;
+int adam_path_from_name(const char *e) {
+    if (!e) return 0;
+    if (strcmp(e, "tma") == 0) return 1;
+    if (strcmp(e, "tma256x2") == 0) return 2;
+    if (strcmp(e, "tma512x3") == 0) return 3;
+    if (strcmp(e, "ws16") == 0) return 4;
+    if (strcmp(e, "ws8") == 0) return 5;
+    return 0;
+}
+
 }  // namespace
 }  // namespace gg
+
+extern "C" int gg_set_adam_path(const char *name) {
+    gg::g_adam_path = gg::adam_path_from_name(name);
+    return 0;
+}
 
 extern "C" int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias,
                              float *m_bias, float *v_bias, const int32_t *n_unique, const int32_t *uniq_ids,
                              const float *grad_rows, const float *grad_bias, int32_t *row_slot, float lr_t, float beta1,
                              float beta2, float eps, void *stream) {
     (void)n_unique; (void)uniq_ids;
-    static int use_tma = -1;       // GG_ADAM_PATH=tma[...] selects the cp.async.bulk pipeline (A/B measurement)
-    if (use_tma < 0) {
-        const char *e = getenv("GG_ADAM_PATH");
-        use_tma = 0;                          // default: the per-thread-load sweep (faster as measured)
-        if (e && strcmp(e, "tma") == 0) use_tma = 1;            // cp.async.bulk pipeline, 512 threads x 2 CTAs per SM
-        else if (e && strcmp(e, "tma256x2") == 0) use_tma = 2;
-        else if (e && strcmp(e, "tma512x3") == 0) use_tma = 3;
-    }
+    if (gg::g_adam_path < 0) gg::g_adam_path = gg::adam_path_from_name(getenv("GG_ADAM_PATH"));
+    const int use_tma = gg::g_adam_path;
     GG_REQUIRE(emb && m_emb && v_emb && bias && m_bias && v_bias && grad_rows && grad_bias && row_slot, "null pointer");
     GG_REQUIRE(ld == 32 || ld == 64 || ld == 128 || ld == 256, "ld must be 32, 64, 128 or 256 (row stride in floats)");
     if (n_node == 0) return 0;
@@ -169,6 +298,20 @@ extern "C" int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_em
         gg::adam_tma_kernel<NT, MINB><<<(unsigned)blocks, NT, gg::ADAM_TMA_SMEM, st>>>(                                         \
             n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, grad_rows, grad_bias, row_slot, lr_t, beta1, beta2, eps);      \
     } while (0)
+        if (use_tma >= 4) {             // warp-specialised: 16 (or 8) consumer warps + 1 producer warp, 2 CTAs per SM
+            long long blocks = (long long)gg::sm_count() * 2;
+            if (blocks > n_tiles) blocks = n_tiles;
+            if (use_tma == 4) {
+                GG_CHECK(cudaFuncSetAttribute(gg::adam_ws_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gg::ADAM_TMA_SMEM));
+                gg::adam_ws_kernel<16, 2><<<(unsigned)blocks, 17 * 32, gg::ADAM_TMA_SMEM, st>>>(
+                    n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, grad_rows, grad_bias, row_slot, lr_t, beta1, beta2, eps);
+            } else {
+                GG_CHECK(cudaFuncSetAttribute(gg::adam_ws_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gg::ADAM_TMA_SMEM));
+                gg::adam_ws_kernel<8, 2><<<(unsigned)blocks, 9 * 32, gg::ADAM_TMA_SMEM, st>>>(
+                    n_node, ld, emb, m_emb, v_emb, bias, m_bias, v_bias, grad_rows, grad_bias, row_slot, lr_t, beta1, beta2, eps);
+            }
+            return gg::check_cuda(cudaGetLastError(), "adam (warp-specialised TMA) kernel launch");
+        }
         if (use_tma == 2) GG_ADAM_TMA(256, 2);
         else if (use_tma == 3) GG_ADAM_TMA(512, 3);
         else GG_ADAM_TMA(512, 2);

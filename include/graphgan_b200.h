@@ -252,6 +252,10 @@ int gg_dp_train_steps(void *comm, int32_t mode, int64_t n_rows, const int64_t *s
 /* K3: TF1.8 AdamOptimizer sparse apply == dense decay (generator.py:30-31,
  * discriminator.py:31-32): m <- b1*m (+ (1-b1) g on touched rows), v likewise, then for ALL
  * rows var -= lr_t * m / (sqrt(v) + eps).  Resets row_slot to -1. */
+/* Selects the kernel behind gg_adam_apply (identical results): "ldg" per-thread loads (default), "tma" / "tma256x2" /
+ * "tma512x3" cp.async.bulk pipeline with a CTA barrier per tile, "ws16" / "ws8" warp-specialised cp.async.bulk pipeline.
+ * The environment variable GG_ADAM_PATH sets the initial choice. */
+int gg_set_adam_path(const char *name);
 int gg_adam_apply(int64_t n_node, int32_t ld, float *emb, float *m_emb, float *v_emb, float *bias,
                   float *m_bias, float *v_bias, const int32_t *n_unique, const int32_t *uniq_ids,
                   const float *grad_rows, const float *grad_bias, int32_t *row_slot, float lr_t,

@@ -383,3 +383,78 @@ def test_device_link_prediction_and_binary_dump(cuda_device, tmp_path, monkeypat
     assert abs(acc - want) < 1e-9
     print("dump+eval at N=1M: %.3f s" % dt)
     assert dt < 1.5
+
+
+def test_level1_integration_reference_loop_over_the_session_shim(cuda_device):
+    """INTEGRATION.md "Level 1": the reference's own per-root sampling loop (graph_gan.py:182-291, restated without
+    changes in oracle/faithful.py and proven equal to the unmodified reference on this fixture) with its TensorFlow
+    fetches answered by the ``Session.run(fetch, feed_dict)`` shim -- ``generator.all_score`` (graph_gan.py:238),
+    ``discriminator.reward`` (:220-222), then ``d_updates`` / ``g_updates`` (:154-157, :173-176) fed exactly as the
+    reference feeds them.  With the fixture's MT19937 stream the loop must reproduce the reference's own
+    prepare_data_for_d rows and generator pairs, and the fed update steps must match the numpy oracle."""
+    from graphgan_b200.discriminator import Discriminator
+    from graphgan_b200.generator import Generator
+    from graphgan_b200.session import Session
+    from oracle import faithful, updates
+    c = loader.load("rand300")
+    gen = Generator(c.n, c.emb_g, device=cuda_device)
+    gen.bias_t.copy_(__import__("torch").as_tensor(c.bias_g))
+    dis = Discriminator(c.n, c.emb_d, device=cuda_device)
+    dis.bias_t.copy_(__import__("torch").as_tensor(c.bias_d))
+    sess = Session()
+
+    class Level1(faithful.Faithful):          # the two fetches of the sampling loop go through the shim
+        def all_score(self):
+            return sess.run(gen.all_score)
+        def reward(self, node_1, node_2):
+            return sess.run(dis.reward, feed_dict={dis.node_id: np.array(node_1), dis.node_neighbor_id: np.array(node_2)})
+
+    F = Level1(c.graph, c.emb_g, c.bias_g, c.emb_d, c.bias_d, rng=np.random.RandomState(int(c.seed)), score_mode="literal",
+               trees=faithful.build_trees(c.graph, range(c.n)))
+    ce, ne, la = F.prepare_data_for_d()
+    assert np.array_equal(ce, c.d_center) and np.array_equal(ne, c.d_neighbor) and np.array_equal(la, c.d_labels)
+    n1, n2, rw = F.prepare_data_for_g(n_sample_gen=int(c.n_sample_gen))
+    k = c.g_node_1.shape[0]
+    assert len(n1) == int(c.g_n_pairs) and np.array_equal(n1[:k], c.g_node_1) and np.array_equal(n2[:k], c.g_node_2)
+    assert np.allclose(rw[:k], c.g_reward, rtol=1e-5, atol=5e-6)
+    # the update call sites, fed like graph_gan.py:154-157 / 173-176
+    od, og = updates.Discriminator(c.n, c.emb_d, 1e-3, 1e-5, bias_init=c.bias_d), updates.Generator(c.n, c.emb_g, 1e-3, 1e-5, bias_init=c.bias_g)
+    for start in range(0, 256, 64):
+        end = start + 64
+        sess.run(dis.d_updates, feed_dict={dis.node_id: np.array(ce[start:end]), dis.node_neighbor_id: np.array(ne[start:end]),
+                                           dis.label: np.array(la[start:end])})
+        od.d_updates(np.array(ce[start:end]), np.array(ne[start:end]), np.array(la[start:end], np.float32))
+        sess.run(gen.g_updates, feed_dict={gen.node_id: np.array(n1[start:end]), gen.node_neighbor_id: np.array(n2[start:end]),
+                                           gen.reward: np.array(rw[start:end])})
+        og.g_updates(np.array(n1[start:end]), np.array(n2[start:end]), np.array(rw[start:end], np.float32))
+    assert close(sess.run(dis.embedding_matrix), od.E, steps=4) and close(sess.run(gen.embedding_matrix), og.E, steps=4)
+
+
+@pytest.mark.parametrize("n,d", [(3000, 128), (700, 50), (257, 256), (64, 32), (40000, 128)])
+def test_adam_sweep_variants_are_bit_identical(n, d, cuda_device):
+    """K3 has three implementations behind gg_adam_apply: per-thread loads (default), a cp.async.bulk pipeline with a CTA
+    barrier per tile, and a warp-specialised cp.async.bulk pipeline (producer warp + consumer warps on mbarriers).  Same
+    per-element operation sequence, so every state tensor must be bit-identical after several steps -- including partial
+    last tiles, rows with gradients, the bias update and the slot map reset."""
+    import torch
+    from graphgan_b200 import _cabi
+    from graphgan_b200.discriminator import Discriminator
+    lib = _cabi.lib()
+    rs = np.random.RandomState(n + d)
+    emb = rs.normal(0, 0.5, size=(n, d))
+    batches = [(b[0], b[1], (rs.random_sample(64) < 0.5).astype(np.float32)) for b in _batches(rs, n, 5, 64)]
+    got = {}
+    try:
+        for path in ("ldg", "tma", "tma256x2", "tma512x3", "ws16", "ws8"):
+            lib.gg_set_adam_path(path.encode())
+            m = Discriminator(n, emb, device=cuda_device)
+            for i, j, lab in batches:
+                m.d_step(i, j, lab)
+            torch.cuda.synchronize()
+            got[path] = {k: getattr(m, k).clone() for k in ("emb", "m_emb", "v_emb", "bias_t", "m_bias", "v_bias", "row_slot")}
+    finally:
+        lib.gg_set_adam_path(b"ldg")
+    for path, st in got.items():
+        for k, v in st.items():
+            assert torch.equal(v, got["ldg"][k]), (path, k)
+    assert int((got["ldg"]["row_slot"] != -1).sum()) == 0
