@@ -16,8 +16,9 @@
 //   * the level's frontier is consumed in CHUNKS of consecutive queue entries holding <= 8192 adjacency entries,
 //     8 consecutive entries per thread (one 32-B sector);
 //   * inside a chunk, several frontier nodes may reach the same undiscovered node: every candidate entry proposes
-//     key = (chunk-local index of its source, tag of the head) with atomicMin into a 16 k-slot shared table indexed
-//     by the head's low bits.  After a barrier the slot's minimum decides: same key -> this entry is THE tree edge;
+//     key = (chunk-local index of its source, tag of the head) into a 16 k-slot shared table indexed by the head's low
+//     bits, keeping the minimum (plain load / compare / store iterated to a fixed point: shared-memory atomics are the
+//     slower way).  After a barrier the slot's minimum decides: same key -> this entry is THE tree edge;
 //     same head, other key -> an earlier father won; other head -> hash collision, the entry stays pending and the
 //     round repeats (rare: the table is at most half full).  Earlier chunks have already set their winners' visited
 //     bits, so "first in queue order" holds across chunks as well;
@@ -33,21 +34,19 @@
 namespace gg {
 namespace {
 
-constexpr int BFS_THREADS = 512;
-constexpr int BFS_WARPS = BFS_THREADS / 32;
-constexpr int BFS_EPT = 16;                                // adjacency entries per thread per slab
+constexpr int BFS_THREADS = 1024;
+constexpr int BFS_EPT = 8;                                 // adjacency entries per thread per slab
 constexpr unsigned BFS_SLAB = BFS_THREADS * BFS_EPT;       // 8192 entries
-constexpr int BFS_WIN = 2 * BFS_THREADS;                   // frontier nodes per window (two per thread)
 constexpr int BFS_HBITS = 14;
 constexpr unsigned BFS_HSLOTS = 1u << BFS_HBITS;           // 16384 slots, 64 KB
 constexpr unsigned BFS_EMPTY = 0xffffffffu;
 constexpr unsigned BFS_BU_MAX = BFS_HSLOTS / 2;             // bottom-up levels sort <= 8192 64-bit keys in the table's memory
 // shared memory: table | start[1025] | a0[1024] | warp totals[2][32] | pad | bitmap
-constexpr unsigned BFS_FIXED_WORDS = BFS_HSLOTS + (BFS_WIN + 1) + BFS_WIN + 64 + 31;
+constexpr unsigned BFS_FIXED_WORDS = BFS_HSLOTS + (BFS_THREADS + 1) + BFS_THREADS + 64 + 31;
 constexpr long long BFS_SMEM_MAX_BYTES = 227 * 1024;
 constexpr long long BFS_SMEM_BITMAP_MAX_BYTES = BFS_SMEM_MAX_BYTES - 4ll * BFS_FIXED_WORDS;
 
-// inclusive block scan (BFS_THREADS threads); `total` = sum over the block.  Two barriers; consecutive calls must alternate
+// inclusive block scan (1024 threads); `total` = sum over the block.  Two barriers; consecutive calls must alternate
 // between the two halves of s_tot (a fast warp's next scan may not overwrite totals a slow warp still reads).
 __device__ __forceinline__ unsigned block_scan_incl(unsigned v, unsigned *s_tot, unsigned &total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -59,7 +58,7 @@ __device__ __forceinline__ unsigned block_scan_incl(unsigned v, unsigned *s_tot,
     }
     if (lane == 31) s_tot[wid] = x;
     __syncthreads();
-    unsigned t = lane < BFS_WARPS ? s_tot[lane] : 0u;       // every warp scans the warp totals itself
+    unsigned t = s_tot[lane];                               // every warp scans the 32 warp totals itself
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const unsigned y = __shfl_up_sync(FULL, t, off);
@@ -67,7 +66,7 @@ __device__ __forceinline__ unsigned block_scan_incl(unsigned v, unsigned *s_tot,
     }
     total = __shfl_sync(FULL, t, 31);
     const unsigned add = __shfl_sync(FULL, t, (wid + 31) & 31);
-    return x + (wid ? add : 0u);   // (total: lanes >= BFS_WARPS carry the last warp's inclusive value)
+    return x + (wid ? add : 0u);
 }
 
 template <bool VSMEM>
@@ -83,9 +82,9 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
            unsigned *__restrict__ posbuf, unsigned *__restrict__ gbitmap, int tagbits, unsigned avg_deg) {
     extern __shared__ __align__(16) unsigned bfs_smem[];
     unsigned *table = bfs_smem;
-    unsigned *start = table + BFS_HSLOTS;                  // [WIN + 1] exclusive prefix of the window's degrees
-    unsigned *a0s = start + BFS_WIN + 1;                   // [WIN] first walk-CSR entry of the window's nodes
-    unsigned *s_tot = a0s + BFS_WIN;                       // [2][32]
+    unsigned *start = table + BFS_HSLOTS;                  // [1025] exclusive prefix of the window's degrees
+    unsigned *a0s = start + BFS_THREADS + 1;               // [1024] first walk-CSR entry of the window's nodes
+    unsigned *s_tot = a0s + BFS_THREADS;                   // [2][32]
     unsigned *s_win = s_tot + 64;                          // "this slab discovered something" flag
     const size_t bm_words = ((size_t)n_node + 31) / 32;
     unsigned *V = VSMEM ? (s_tot + 64 + 31) : (gbitmap + (size_t)blockIdx.x * bm_words);
@@ -184,143 +183,164 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                 continue;
             }
             unsigned pf_i = 0xffffffffu;                    // prefetched window (valid inside a level only)
-            uint2 pf0 = make_uint2(0u, 0u), pf1 = make_uint2(0u, 0u);
-            for (unsigned wbase = lo; wbase < hi; wbase += BFS_WIN) {
-                // ---- window: the next <= 1024 frontier nodes (two per thread).  ONE scan numbers all their adjacency
-                // entries; the window is then swept in fixed slabs of SLAB consecutive entries of that numbering, 16
-                // consecutive entries per thread -- a node may straddle slabs (its own entries never collide, and the
-                // heads the earlier slab claimed are already marked visited).
-                const unsigned nvalid = (hi - wbase) < (unsigned)BFS_WIN ? (hi - wbase) : (unsigned)BFS_WIN;
-                uint2 q0 = make_uint2(0u, 0u), q1 = make_uint2(0u, 0u);
-                if (pf_i == wbase) { q0 = pf0; q1 = pf1; }
-                else {
-                    if (2u * tid < nvalid) q0 = Q[wbase + 2 * tid];
-                    if (2u * tid + 1 < nvalid) q1 = Q[wbase + 2 * tid + 1];
-                }
-                pf_i = wbase + BFS_WIN;                     // the next window of this level (written during the previous
-                pf0 = pf1 = make_uint2(0u, 0u);             // level): in flight while this one is processed
-                if (pf_i + 2 * tid < hi) pf0 = Q[pf_i + 2 * tid];
-                if (pf_i + 2 * tid + 1 < hi) pf1 = Q[pf_i + 2 * tid + 1];
-                unsigned total;
-                const unsigned incl = block_scan_incl(q0.y + q1.y, s_tot + 32 * (flip ^= 1u), total);
-                const unsigned ex = incl - q0.y - q1.y;
-                start[2 * tid] = ex; start[2 * tid + 1] = ex + q0.y;
-                a0s[2 * tid] = q0.x; a0s[2 * tid + 1] = q1.x;
-                if (tid == BFS_THREADS - 1) start[BFS_WIN] = incl;
+            uint2 pf = make_uint2(0u, 0u);
+            for (unsigned wbase = lo; wbase < hi; wbase += BFS_THREADS) {
+                // ---- window: the next <= 1024 frontier nodes; ONE scan numbers all their adjacency entries, the
+                // chunks (<= SLAB entries each) are then cut out of that numbering
+                const unsigned nvalid = (hi - wbase) < (unsigned)BFS_THREADS ? (hi - wbase) : (unsigned)BFS_THREADS;
+                uint2 q = make_uint2(0u, 0u);
+                if (pf_i == wbase) q = pf;
+                else if ((unsigned)tid < nvalid) q = Q[wbase + tid];
+                pf_i = wbase + BFS_THREADS;                 // the next window of this level (written during the previous
+                pf = make_uint2(0u, 0u);                    // level): in flight while this one is processed
+                if (pf_i + tid < hi) pf = Q[pf_i + tid];
+                unsigned tot;
+                const unsigned incl = block_scan_incl(q.y, s_tot + 32 * (flip ^= 1u), tot);
+                start[tid] = incl - q.y; a0s[tid] = q.x;
+                if (tid == BFS_THREADS - 1) start[BFS_THREADS] = incl;
                 __syncthreads();
-                const unsigned nslab = (total + BFS_SLAB - 1) / BFS_SLAB;
-
-                // heads (w) and owners (j, 16 bits each) of my 16 entries of slab sl: the loads fly while the previous
-                // slab is resolved
-                auto load_slab = [&](unsigned sl, int (&w)[BFS_EPT], unsigned (&jp)[BFS_EPT / 2]) {
-                    const unsigned K0 = sl * BFS_SLAB + (unsigned)tid * BFS_EPT;
+                unsigned jlo = 0;
+                while (jlo < nvalid) {                      // chunks of consecutive frontier nodes
+                    const unsigned base = start[jlo];
+                    unsigned m = (unsigned)__syncthreads_count((unsigned)tid >= jlo && (unsigned)tid < nvalid &&
+                                                               start[tid + 1] - base <= BFS_SLAB);   // a prefix of [jlo, nvalid)
+                    if (m == 0) m = 1;                      // one node with more than SLAB entries: a chunk of its own
+                    if (tid == 0) *s_win = 0u;              // (the previous chunk's readers are behind the barrier above)
+                    const unsigned Kend = start[jlo + m];   // entries [base, Kend) in the window's numbering
+                    const bool single = (m == 1);           // a node's own entries never collide: no table needed
+                    for (unsigned s0 = base; s0 < Kend; s0 += BFS_SLAB) {
+                        const unsigned K0 = s0 + (unsigned)tid * BFS_EPT;
+                        unsigned ee[BFS_EPT], key[BFS_EPT];
+                        int w[BFS_EPT];
 #pragma unroll
-                    for (int x = 0; x < BFS_EPT; ++x) w[x] = -1;
-#pragma unroll
-                    for (int x = 0; x < BFS_EPT / 2; ++x) jp[x] = 0u;
-                    if (K0 >= total) return;
-                    unsigned l = 0, h = nvalid - 1;         // owner of entry K0: last j with start[j] <= K0
-                    while (l < h) {
-                        const unsigned mid = (l + h + 1) >> 1;
-                        if (start[mid] <= K0) l = mid; else h = mid - 1;
-                    }
-                    unsigned j = l, nxt = start[j + 1], base = a0s[j] - start[j];
-#pragma unroll
-                    for (int x = 0; x < BFS_EPT; ++x) {
-                        const unsigned K = K0 + x;
-                        if (K < total) {
-                            while (K >= nxt) { ++j; nxt = start[j + 1]; base = a0s[j] - start[j]; }
-                            w[x] = __ldg(adj + (base + K));
-                            jp[x >> 1] |= j << (16 * (x & 1));
-                        }
-                    }
-                };
-                auto process_slab = [&](unsigned sl, int (&w)[BFS_EPT], unsigned (&jp)[BFS_EPT / 2]) {
-                    const unsigned K0 = sl * BFS_SLAB + (unsigned)tid * BFS_EPT;
-                    if (tid == 0) *s_win = 0u;              // (the previous slab's readers are behind a barrier)
-                    unsigned cm = 0;                        // candidate entries: head not discovered yet
-#pragma unroll
-                    for (int x = 0; x < BFS_EPT; ++x)
-                        if (w[x] >= 0 && !v_test<VSMEM>(V, w[x])) cm |= 1u << x;
-                    unsigned wm = 0, pend = cm;             // winners: the tree edges among my entries
-                    for (;;) {
-                        if (pend) {
-#pragma unroll
-                            for (int x = 0; x < BFS_EPT; ++x)
-                                if ((pend >> x) & 1u) {
-                                    const unsigned key = (((jp[x >> 1] >> (16 * (x & 1))) & 0xffffu) << tagbits) |
-                                                         (((unsigned)w[x] >> BFS_HBITS) & tagmask);
-                                    atomicMin(table + ((unsigned)w[x] & (BFS_HSLOTS - 1)), key);
+                        for (int x = 0; x < BFS_EPT; ++x) { ee[x] = 0xffffffffu; key[x] = 0; }
+                        if (K0 < Kend) {
+                            unsigned j = jlo;
+                            if (!single) {                  // owner of entry K0: last j in the chunk with start[j] <= K0
+                                unsigned l = jlo, h = jlo + m - 1;
+                                while (l < h) {
+                                    const unsigned mid = (l + h + 1) >> 1;
+                                    if (start[mid] <= K0) l = mid; else h = mid - 1;
                                 }
-                        }
-                        __syncthreads();
-                        unsigned still = 0;
-                        if (pend) {
+                                j = l;
+                            }
+                            unsigned nxt = start[j + 1];
+                            if (K0 + BFS_EPT <= nxt) {      // all my entries belong to one node (the common case)
+                                const unsigned e0 = a0s[j] + (K0 - start[j]);
 #pragma unroll
-                            for (int x = 0; x < BFS_EPT; ++x) {
-                                if (!((pend >> x) & 1u)) continue;
-                                const unsigned key = (((jp[x >> 1] >> (16 * (x & 1))) & 0xffffu) << tagbits) |
-                                                     (((unsigned)w[x] >> BFS_HBITS) & tagmask);
-                                const unsigned t = table[(unsigned)w[x] & (BFS_HSLOTS - 1)];
-                                if (t == key) {
-                                    wm |= 1u << x;
-                                    atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
-                                } else if ((t & tagmask) != (key & tagmask)) {
-                                    still |= 1u << x;       // the slot went to another head: try again
+                                for (int x = 0; x < BFS_EPT; ++x) { ee[x] = e0 + x; key[x] = (j - jlo) << tagbits; }
+                            } else {
+#pragma unroll
+                                for (int x = 0; x < BFS_EPT; ++x) {
+                                    const unsigned K = K0 + x;
+                                    if (K < Kend) {
+                                        while (K >= nxt) { ++j; nxt = start[j + 1]; }   // (skips empty nodes; K < Kend bounds j)
+                                        ee[x] = a0s[j] + (K - start[j]);
+                                        key[x] = (j - jlo) << tagbits;
+                                    }
                                 }
                             }
-                            if (wm) *s_win = 1u;
                         }
-                        const int any = __syncthreads_or(still != 0u);
-                        if (pend) {
 #pragma unroll
-                            for (int x = 0; x < BFS_EPT; ++x)
-                                if ((pend >> x) & 1u) table[(unsigned)w[x] & (BFS_HSLOTS - 1)] = BFS_EMPTY;
+                        for (int x = 0; x < BFS_EPT; ++x) w[x] = (ee[x] != 0xffffffffu) ? __ldg(adj + ee[x]) : -1;
+                        unsigned cm = 0;                    // candidate entries: head not discovered yet
+#pragma unroll
+                        for (int x = 0; x < BFS_EPT; ++x)
+                            if (w[x] >= 0 && !v_test<VSMEM>(V, w[x])) cm |= 1u << x;
+                        unsigned wm = 0;                    // winners: the tree edges among my entries
+                        int anyw;
+                        if (single) {
+                            wm = cm;
+                            if (cm) {
+#pragma unroll
+                                for (int x = 0; x < BFS_EPT; ++x)
+                                    if ((cm >> x) & 1u) atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
+                            }
+                            anyw = __syncthreads_or(wm != 0u);
+                        } else {
+                            unsigned pend = cm;
+                            if (cm) {
+#pragma unroll
+                                for (int x = 0; x < BFS_EPT; ++x) key[x] |= ((unsigned)w[x] >> BFS_HBITS) & tagmask;
+                            }
+                            for (;;) {
+                                // slot minimum WITHOUT atomics (shared-memory atomics cost ~2 cycles per lane, plain LDS / STS
+                                // a fraction of that): every candidate whose key is below the slot's value stores it; stores
+                                // race, so repeat until nobody had to store -- then every slot holds its minimum (the owner of
+                                // a smaller key would still be storing).  One contender per slot drops out per iteration.
+                                {
+                                    unsigned act = pend;
+                                    for (;;) {
+                                        unsigned wrote = 0;
+                                        if (act) {
+#pragma unroll
+                                            for (int x = 0; x < BFS_EPT; ++x) {
+                                                if (!((act >> x) & 1u)) continue;
+                                                volatile unsigned *slot = table + ((unsigned)w[x] & (BFS_HSLOTS - 1));
+                                                if (key[x] < *slot) { *slot = key[x]; wrote |= 1u << x; }
+                                                else act &= ~(1u << x);
+                                            }
+                                        }
+                                        if (!__syncthreads_or(wrote != 0u)) break;
+                                    }
+                                }
+                                unsigned still = 0;
+                                if (pend) {
+#pragma unroll
+                                    for (int x = 0; x < BFS_EPT; ++x) {
+                                        if (!((pend >> x) & 1u)) continue;
+                                        const unsigned t = table[(unsigned)w[x] & (BFS_HSLOTS - 1)];
+                                        if (t == key[x]) {
+                                            wm |= 1u << x;
+                                            atomicOr(V + (w[x] >> 5), 1u << (w[x] & 31));
+                                        } else if ((t & tagmask) != (key[x] & tagmask)) {
+                                            still |= 1u << x;   // the slot went to another head: try again
+                                        }
+                                    }
+                                    if (wm) *s_win = 1u;
+                                }
+                                const int any = __syncthreads_or(still != 0u);
+                                if (pend) {
+#pragma unroll
+                                    for (int x = 0; x < BFS_EPT; ++x)
+                                        if ((pend >> x) & 1u) table[(unsigned)w[x] & (BFS_HSLOTS - 1)] = BFS_EMPTY;
+                                }
+                                pend = still;
+                                if (!any) break;
+                                __syncthreads();
+                            }
+                            anyw = (int)*s_win;
                         }
-                        pend = still;
-                        if (!any) break;
+                        if (!anyw) continue;                // (uniform) nothing discovered by this slab: no compaction
+                        // ---- winners in entry order = FIFO order.  They are sparse (a few per cent of the entries), so
+                        // they are first compacted into the (now idle, all-EMPTY) table as (head, entry) pairs at their FIFO
+                        // index, then handled one per thread: entry range of the node -> queue, queue position, tree bit.
+                        unsigned ntot;
+                        const unsigned cnt = (unsigned)__popc(wm);
+                        unsigned li = block_scan_incl(cnt, s_tot + 32 * (flip ^= 1u), ntot) - cnt;
+                        if (wm) {
+#pragma unroll
+                            for (int x = 0; x < BFS_EPT; ++x) {
+                                if (!((wm >> x) & 1u)) continue;
+                                table[2 * li] = (unsigned)w[x];
+                                table[2 * li + 1] = ee[x];
+                                ++li;
+                            }
+                        }
                         __syncthreads();
-                    }
-                    if (!*s_win) { __syncthreads(); return; }   // (uniform) nothing discovered by this slab
-                    // ---- winners in entry order = FIFO order.  They are sparse (a few per cent of the entries), so
-                    // they are first compacted into the (now idle, all-EMPTY) table as (head, entry) pairs at their FIFO
-                    // index, then handled one per thread: entry range of the node -> queue, queue position, tree bit.
-                    unsigned ntot;
-                    const unsigned cnt = (unsigned)__popc(wm);
-                    unsigned li = block_scan_incl(cnt, s_tot + 32 * (flip ^= 1u), ntot) - cnt;
-                    if (wm) {
-#pragma unroll
-                        for (int x = 0; x < BFS_EPT; ++x) {
-                            if (!((wm >> x) & 1u)) continue;
-                            const unsigned j = (jp[x >> 1] >> (16 * (x & 1))) & 0xffffu;
-                            table[2 * li] = (unsigned)w[x];
-                            table[2 * li + 1] = a0s[j] + (K0 + x - start[j]);
-                            ++li;
+                        for (unsigned i = tid; i < ntot; i += BFS_THREADS) {
+                            const unsigned wv = table[2 * i], e = table[2 * i + 1];
+                            table[2 * i] = BFS_EMPTY; table[2 * i + 1] = BFS_EMPTY;
+                            const unsigned qa = ip32[2 * (size_t)wv], qb = ip32[2 * (size_t)wv + 2];
+                            Q[tail + i] = make_uint2(qa, qb - qa);
+                            pos[wv] = tail + i;
+                            deg_acc += qb - qa;
+                            atomicOr(tb + (e >> 5), 1u << (e & 31));
                         }
+                        tail += ntot;
+                        if (single && s0 + BFS_SLAB < Kend) __syncthreads();   // next slab of the same node: *s_win is not used
                     }
-                    __syncthreads();
-                    for (unsigned i = tid; i < ntot; i += BFS_THREADS) {
-                        const unsigned wv = table[2 * i], e = table[2 * i + 1];
-                        table[2 * i] = BFS_EMPTY; table[2 * i + 1] = BFS_EMPTY;
-                        const unsigned qa = ip32[2 * (size_t)wv], qb = ip32[2 * (size_t)wv + 2];
-                        Q[tail + i] = make_uint2(qa, qb - qa);
-                        pos[wv] = tail + i;
-                        deg_acc += qb - qa;
-                        atomicOr(tb + (e >> 5), 1u << (e & 31));
-                    }
-                    tail += ntot;
-                    __syncthreads();
-                };
-                int wA[BFS_EPT], wB[BFS_EPT];
-                unsigned jA[BFS_EPT / 2], jB[BFS_EPT / 2];
-                if (nslab) load_slab(0, wA, jA);
-                for (unsigned sl = 0; sl < nslab; sl += 2) {
-                    if (sl + 1 < nslab) load_slab(sl + 1, wB, jB);
-                    process_slab(sl, wA, jA);
-                    if (sl + 1 < nslab) {
-                        if (sl + 2 < nslab) load_slab(sl + 2, wA, jA);
-                        process_slab(sl + 1, wB, jB);
-                    }
+                    jlo += m;
                 }
             }
             {                                               // adjacency entries of the next frontier
