@@ -9,7 +9,7 @@ import os
 from . import _build
 
 _LIB = None
-ABI_VERSION = 2      # == GG_ABI_VERSION of include/graphgan_b200.h
+ABI_VERSION = 3      # == GG_ABI_VERSION of include/graphgan_b200.h
 
 
 class GGError(RuntimeError):
@@ -51,6 +51,8 @@ SIGNATURES = {
     "gg_bfs_scratch_bytes": (C.c_int, [_I64, _I64, C.POINTER(_I64)]),
     "gg_tree_words": (C.c_int, [_I64, C.POINTER(_I64)]),
     "gg_bfs_build": (C.c_int, [_I64, _I64, _P, _P, _I64, _P, _P, _I64, _P, _I64, _P]),
+    "gg_reverse_entries": (C.c_int, [_I64, _I64, _P, _P, _P, _P, _P]),
+    "gg_bfs_build_ex": (C.c_int, [_I64, _I64, _P, _P, _P, _I64, _P, _P, _I64, _P, _I64, C.c_float, C.c_int32, _P]),
     "gg_tree_parent": (C.c_int, [_I64, _P, _P, _I64, _P, _P, _I64, _P, _P]),
     "gg_pair_reward": (C.c_int, [_I64, _P, _P, _P, _P, _I32, _P, _P]),
     "gg_all_score": (C.c_int, [_I64, _P, _P, _I32, _P, _P]),

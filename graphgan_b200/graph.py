@@ -109,6 +109,20 @@ class DeviceGraph:
         self.n_bit_words = (host.adj.shape[0] + 31) // 32 + 1
         self.d1_bits = torch.zeros(self.n_bit_words, dtype=torch.int32, device=self.device)
 
+    def reverse_entries(self):
+        """rev[e] = index of the entry (v -> u) for e = (u -> v) (gg_reverse_entries; device int32 [nnz], cached), or None
+        when the walk CSR is not symmetric -- the tree builder then stays top-down (csrc/bfs.cu)."""
+        import torch
+        if not hasattr(self, "_rev"):
+            nnz = int(self.host.adj.shape[0])
+            rev = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)
+            missing = torch.zeros(1, dtype=torch.int32, device=self.device)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _cabi.check(_cabi.lib().gg_reverse_entries(self.n_node, nnz, self.indptr.data_ptr(), self.adj.data_ptr(),
+                                                       rev.data_ptr(), missing.data_ptr(), st), "gg_reverse_entries")
+            self._rev = rev if int(missing.item()) == 0 else None
+        return self._rev
+
     def hub_tiles(self, threshold, tile_edges=256):
         """Work list of gg_hub_scores: (node, first entry) of every `tile_edges`-entry slice of the
         adjacency of nodes whose walk-CSR degree is >= threshold.  Static per graph; cached."""

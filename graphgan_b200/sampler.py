@@ -6,6 +6,7 @@ launch.  Torch tensors are used purely as device-memory containers; all computat
 in libgraphgan_b200.so through the C ABI (include/graphgan_b200.h).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -181,6 +182,10 @@ class WalkSampler:
         self.scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
         self.work_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._bfs_scratch = None
+        # tree builder: direction-optimising BFS (csrc/bfs.cu).  < 0: library default ratio, 0: top-down + small sorted
+        # bottom-up levels only; the trees are identical in every mode (tests/test_walk_gpu.py)
+        self.bfs_bottom_up_ratio = float(os.environ.get("GG_BFS_BU_RATIO", "-1"))
+        self.bfs_flags = 0
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -199,9 +204,12 @@ class WalkSampler:
             nbytes = C.c_int64(0)
             _cabi.check(self.lib.gg_bfs_scratch_bytes(N, int(self.g.adj.shape[0]), C.byref(nbytes)), "gg_bfs_scratch_bytes")
             self._bfs_scratch = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=self.device)
-        _cabi.check(self.lib.gg_bfs_build(N, nnz, ptr(self.g.indptr), ptr(self.g.adj), R, ptr(roots_d), ptr(tree_bits),
-                                          words.value, ptr(self._bfs_scratch), self._bfs_scratch.numel(), self._stream()),
-                    "gg_bfs_build")
+        rev = self.g.reverse_entries() if self.bfs_bottom_up_ratio != 0.0 else None
+        _cabi.check(self.lib.gg_bfs_build_ex(N, nnz, ptr(self.g.indptr), ptr(self.g.adj), ptr(rev) if rev is not None else None,
+                                             R, ptr(roots_d), ptr(tree_bits), words.value, ptr(self._bfs_scratch),
+                                             self._bfs_scratch.numel(), float(self.bfs_bottom_up_ratio), int(self.bfs_flags),
+                                             self._stream()),
+                    "gg_bfs_build_ex")
         return TreeBatch(roots_d, tree_bits, self.g)
 
     # ------------------------------------------------------------------ K1

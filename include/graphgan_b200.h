@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GG_ABI_VERSION 2
+#define GG_ABI_VERSION 3
 
 /* walk status codes (per walk) */
 enum { GG_NOTRUN = 0, GG_DONE = 1, GG_VOID = 2, GG_SKIPPED = 3 };
@@ -173,6 +173,19 @@ int gg_bfs_scratch_bytes(int64_t n_node, int64_t nnz, int64_t *bytes);
 int gg_bfs_build(int64_t n_node, int64_t nnz, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
                  const int32_t *roots, uint32_t *tree_bits, int64_t tree_words, void *scratch,
                  int64_t scratch_bytes, void *stream);
+/* Direction-optimising form.  rev (device [nnz], gg_reverse_entries; static per graph) maps the entry (u -> v) to the
+ * entry (v -> u) and lets a level run bottom-up: every undiscovered node picks the visited neighbour with the smallest
+ * queue position, the tree row then yields the new nodes in FIFO order (csrc/bfs.cu).  A level runs bottom-up when
+ * (adjacency entries of the undiscovered nodes + 4 * frontier nodes) < bottom_up_ratio * (adjacency entries of the
+ * frontier); bottom_up_ratio < 0: library default, 0: never.  rev == NULL: plain gg_bfs_build.  The trees are the
+ * same bit for bit in every mode.  gg_reverse_entries sets *n_missing (device) to the number of entries without a
+ * reverse (rev = -1 there): a CSR with n_missing != 0 is not symmetric and must be built with rev == NULL. */
+#define GG_BFS_NO_SORTED_BOTTOM_UP 1   /* flags: disable the small sort-based bottom-up levels (tests / A-B) */
+int gg_reverse_entries(int64_t n_node, int64_t nnz, const int64_t *indptr, const int32_t *adj, int32_t *rev,
+                       int32_t *n_missing, void *stream);
+int gg_bfs_build_ex(int64_t n_node, int64_t nnz, const int64_t *indptr, const int32_t *adj, const int32_t *rev,
+                    int64_t n_roots, const int32_t *roots, uint32_t *tree_bits, int64_t tree_words, void *scratch,
+                    int64_t scratch_bytes, float bottom_up_ratio, int32_t flags, void *stream);
 int gg_tree_parent(int64_t n_node, const int64_t *indptr, const int32_t *adj, int64_t n_roots,
                    const int32_t *roots, const uint32_t *tree_bits, int64_t tree_words, int32_t *parent,
                    void *stream);

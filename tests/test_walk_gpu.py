@@ -204,6 +204,94 @@ def test_hub_lists_use_global_scratch(hub, cuda_device):
         assert cnt["rows_gathered"] < cnt["raw_sum_l"]
 
 
+BFS_MODES = {"top_down": (0.0, 0), "default": (-1.0, 0), "bottom_up_forced": (1e9, 1)}
+
+
+def _trees_in_mode(smp, roots, mode):
+    smp.bfs_bottom_up_ratio, smp.bfs_flags = BFS_MODES[mode]
+    return smp.build_trees(roots)
+
+
+def test_reverse_entries_match_numpy(cuda_device):
+    """gg_reverse_entries: rev[e] of e = (u -> v) is the index of (v -> u); an asymmetric CSR is reported, not used."""
+    import torch
+    from graphgan_b200 import graph as G, synth
+    n = 20000
+    hg = G.HostGraph(synth.power_law(n, 12, seed=21), None, n_node=n)
+    dg = G.DeviceGraph(hg, cuda_device)
+    rev = dg.reverse_entries()
+    assert rev is not None
+    rev = rev.cpu().numpy()
+    src = np.repeat(np.arange(n), np.diff(hg.indptr))
+    assert np.array_equal(hg.adj[rev], src) and np.array_equal(src[rev], hg.adj)
+    # one direction of an edge removed: that entry has no reverse
+    keep = np.ones(hg.adj.shape[0], bool)
+    keep[hg.indptr[5]] = False
+    bad = G.HostGraph.from_arrays(n, hg.raw_indptr, hg.raw_adj,
+                                  np.concatenate([[0], np.cumsum(np.bincount(src[keep], minlength=n))]), hg.adj[keep])
+    assert G.DeviceGraph(bad, cuda_device).reverse_entries() is None
+
+
+@pytest.mark.parametrize("graph", ["rand1200", "power_law_12k", "hub_30k", "path_tail"])
+def test_bfs_bottom_up_levels_build_the_same_trees(graph, cuda_device):
+    """The direction-optimising builder (csrc/bfs.cu: bottom_up_level) against the top-down sweep and the FIFO oracle:
+    identical tree rows bit for bit, with the bottom-up form forced at every level it can run at (ratio 1e9, the small
+    sorted form off), at the library default, and off.  hub_30k: a 30 000-leaf hub two hops from the roots -- more
+    undiscovered nodes than one staging round holds (phase A), a frontier node with more children than the child stage
+    holds and ~940 words of tree bits (phase B long-node path).  path_tail: hundreds of one-node levels."""
+    import torch
+    from graphgan_b200 import graph as G, sampler as S, synth
+    from oracle import canonical as can
+    rs = np.random.RandomState(3)
+    if graph == "rand1200":
+        case = loader.load("rand1200")
+        hg = G.HostGraph(case["train_edges"], case["test_edges"], n_node=case.n)
+        roots = np.arange(case.n, dtype=np.int32)
+    elif graph == "power_law_12k":
+        n = 12000
+        hg = G.HostGraph(synth.power_law(n, 10, seed=5), None, n_node=n)
+        roots = synth.pick_roots(hg.degrees(), 96, seed=6)
+    elif graph == "hub_30k":
+        n = 42000
+        hub = 7
+        leaves = rs.permutation(np.arange(100, 30100))
+        star = np.stack([np.full(leaves.shape[0], hub, np.int64), leaves], 1)
+        extra = synth.power_law(n, 4, seed=8)
+        edges = np.concatenate([star[:9000], extra, star[9000:], np.asarray([[41999, 41998], [41998, hub]])])
+        hg = G.HostGraph(edges, None, n_node=n)
+        roots = np.asarray([41999, 41998, hub, 100, 20000, 35000], np.int32)
+    else:
+        n = 5000
+        path = np.stack([np.arange(3000, 3400), np.arange(3001, 3401)], 1)
+        edges = np.concatenate([synth.power_law(n, 6, seed=11), path, np.asarray([[3000, 17]])])
+        hg = G.HostGraph(edges, None, n_node=n)
+        roots = np.asarray([3400, 3200, 17, 4000], np.int32)
+    dg = G.DeviceGraph(hg, cuda_device)
+    assert dg.reverse_entries() is not None
+    smp = S.WalkSampler(dg)
+    want = can.bfs_parents(hg.indptr, hg.adj, roots)
+    rows = {}
+    for mode in BFS_MODES:
+        t = _trees_in_mode(smp, roots, mode)
+        assert np.array_equal(t.parent_arrays().cpu().numpy(), want), mode
+        rows[mode] = t.tree_bits.cpu().numpy()
+    assert np.array_equal(rows["top_down"], rows["default"]) and np.array_equal(rows["top_down"], rows["bottom_up_forced"])
+
+
+def test_bfs_bottom_up_with_the_global_bitmap(cuda_device):
+    """N = 1.8 M (visited bitmap in global scratch, bfs_kernel<false>), bottom-up forced: hundreds of sparse levels."""
+    from graphgan_b200 import graph as G, sampler as S, synth
+    from oracle import canonical as can
+    n = 1_800_000
+    hg = G.HostGraph(synth.power_law(n, 3, seed=9), None, n_node=n)
+    dg = G.DeviceGraph(hg, cuda_device)
+    smp = S.WalkSampler(dg)
+    roots = synth.pick_roots(hg.degrees(), 4, seed=4)
+    want = can.bfs_parents(hg.indptr, hg.adj, roots)
+    for mode in ("bottom_up_forced", "default"):
+        assert np.array_equal(_trees_in_mode(smp, roots, mode).parent_arrays().cpu().numpy(), want), mode
+
+
 @pytest.mark.parametrize("hub", [0, 256])
 def test_giant_hub_lists_beyond_the_smem_score_buffer(hub, cuda_device):
     """A 3000+-neighbour hub: candidate lists longer than the 2048-score shared buffer and than the 64 tiles
