@@ -54,6 +54,8 @@ def parse():
     p.add_argument("--no-depth1", dest="depth1", action="store_false",
                    help="disable the per-(root, depth-1 child) CDF reuse (csrc/walk.cu: step1_cdf_kernel)")
     p.add_argument("--no-tma", action="store_true", help="enumerate hub lists with plain loads instead of cp.async.bulk staging (A/B)")
+    p.add_argument("--flat-steps", type=int, default=None,
+                   help="level-synchronous walk steps before the persistent kernel (csrc/walk.cu: flat_*_kernel); default: the sampler's")
     p.add_argument("--verify", type=int, default=12, help="roots of the last timed pass re-derived with the C oracle (0 = off)")
     p.add_argument("--verify-seconds", type=float, default=45.0, help="time budget of --verify")
     p.add_argument("--g-steps", type=int, default=5, help="timed generator-mode passes (0 = skip)")
@@ -444,6 +446,8 @@ def run_b200(args):
     hg, emb_h, roots, d = make_inputs(args, rank)
     dg = G.DeviceGraph(hg, dev)
     smp = S.WalkSampler(dg, hub_threshold=args.hub_threshold, depth1=args.depth1, hub_first=not args.file_order, tma=not args.no_tma)
+    if args.flat_steps is not None:
+        smp.flat_steps = args.flat_steps
     emb = S.pad_embedding(emb_h, dev)
     bias = torch.zeros(hg.n_node, dtype=torch.float32, device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)

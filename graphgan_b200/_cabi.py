@@ -34,6 +34,7 @@ class WalkDesc(C.Structure):
         ("hub_threshold", C.c_int32), ("no_tma", C.c_int32), ("walk_slot", C.c_void_p),
         ("s1_nq", C.c_int64), ("s1_slot", C.c_void_p), ("s1_ptr", C.c_void_p), ("s1_cnt", C.c_void_p), ("s1_n", C.c_void_p),
         ("s1_q", C.c_void_p), ("s1_ids", C.c_void_p), ("first_idx", C.c_void_p), ("s1_order", C.c_void_p), ("walk_order", C.c_void_p),
+        ("flat_buf", C.c_void_p), ("flat_bytes", C.c_int64), ("flat_steps", C.c_int32), ("flat_reserved", C.c_int32),
     ]
 
 
@@ -45,6 +46,7 @@ SIGNATURES = {
     "gg_hub_scores": (C.c_int, [_I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P]),
     "gg_root_cdf": (C.c_int, [C.POINTER(WalkDesc), _P, _P, _P]),
     "gg_walk_scratch_bytes": (C.c_int, [_I32, C.POINTER(_I64)]),
+    "gg_walk_flat_bytes": (C.c_int, [_I64, _I32, _I32, C.POINTER(_I64)]),
     "gg_walk_sample": (C.c_int, [C.POINTER(WalkDesc), _P]),
     "gg_walk_finalize": (C.c_int, [_I64, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gg_emit_d_rows": (C.c_int, [_I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

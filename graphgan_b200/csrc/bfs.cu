@@ -34,6 +34,12 @@
 namespace gg {
 namespace {
 
+#ifndef GG_BFS_ATOMIC_MIN
+#define GG_BFS_ATOMIC_MIN 1
+#endif
+#ifndef GG_BFS_DEFER
+#define GG_BFS_DEFER 0
+#endif
 constexpr int BFS_THREADS = 1024;
 constexpr int BFS_EPT = 8;                                 // adjacency entries per thread per slab
 constexpr unsigned BFS_SLAB = BFS_THREADS * BFS_EPT;       // 8192 entries
@@ -445,6 +451,10 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                 lo = hi; hi = tail;
                 continue;
             }
+#if GG_BFS_DEFER
+            unsigned dq_a = 0, dq_b = 0, dq_w = 0, dq_pos = 0;   // this thread's winner of the previous slab (see below)
+            bool dq_valid = false;
+#endif
             unsigned pf_i = 0xffffffffu;                    // prefetched window (valid inside a level only)
             uint2 pf = make_uint2(0u, 0u);
             for (unsigned wbase = lo; wbase < hi; wbase += BFS_THREADS) {
@@ -531,6 +541,16 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                                 // a fraction of that): every candidate whose key is below the slot's value stores it; stores
                                 // race, so repeat until nobody had to store -- then every slot holds its minimum (the owner of
                                 // a smaller key would still be storing).  One contender per slot drops out per iteration.
+#if GG_BFS_ATOMIC_MIN
+                                // (A/B) one shared-memory atomicMin per CANDIDATE entry (a few per cent of the entries) and one
+                                // barrier, instead of the barrier-per-round fixed point
+                                if (pend) {
+#pragma unroll
+                                    for (int x = 0; x < BFS_EPT; ++x)
+                                        if ((pend >> x) & 1u) atomicMin(table + ((unsigned)w[x] & (BFS_HSLOTS - 1)), key[x]);
+                                }
+                                __syncthreads();
+#else
                                 {
                                     unsigned act = pend;
                                     for (;;) {
@@ -547,6 +567,7 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                                         if (!__syncthreads_or(wrote != 0u)) break;
                                     }
                                 }
+#endif
                                 unsigned still = 0;
                                 if (pend) {
 #pragma unroll
@@ -591,7 +612,26 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                             }
                         }
                         __syncthreads();
+#if GG_BFS_DEFER
+                        // (A/B) the winner's adjacency range is a random 8-byte read that misses L2 more often than not: it is
+                        // issued here and CONSUMED one slab later (dq_*), behind the next slab's adjacency loads and table rounds
+                        if (dq_valid) {
+                            Q[dq_pos] = make_uint2(dq_a, dq_b - dq_a);
+                            pos[dq_w] = dq_pos;
+                            deg_acc += dq_b - dq_a;
+                            dq_valid = false;
+                        }
+                        if ((unsigned)tid < ntot) {
+                            const unsigned wv = table[2 * tid], e = table[2 * tid + 1];
+                            table[2 * tid] = BFS_EMPTY; table[2 * tid + 1] = BFS_EMPTY;
+                            dq_a = ip32[2 * (size_t)wv]; dq_b = ip32[2 * (size_t)wv + 2];
+                            dq_w = wv; dq_pos = tail + (unsigned)tid; dq_valid = true;
+                            atomicOr(tb + (e >> 5), 1u << (e & 31));
+                        }
+                        for (unsigned i = tid + BFS_THREADS; i < ntot; i += BFS_THREADS) {
+#else
                         for (unsigned i = tid; i < ntot; i += BFS_THREADS) {
+#endif
                             const unsigned wv = table[2 * i], e = table[2 * i + 1];
                             table[2 * i] = BFS_EMPTY; table[2 * i + 1] = BFS_EMPTY;
                             const unsigned qa = ip32[2 * (size_t)wv], qb = ip32[2 * (size_t)wv + 2];
@@ -601,11 +641,25 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                             atomicOr(tb + (e >> 5), 1u << (e & 31));
                         }
                         tail += ntot;
+#if GG_BFS_ATOMIC_MIN
+                        // the table reads / resets above must be over before the next slab's atomicMin proposals (the fixed-point
+                        // loop re-stores a proposal that a late reset wiped; a single atomicMin cannot)
+                        if (!single || s0 + BFS_SLAB < Kend) __syncthreads();
+#else
                         if (single && s0 + BFS_SLAB < Kend) __syncthreads();   // next slab of the same node: *s_win is not used
+#endif
                     }
                     jlo += m;
                 }
             }
+#if GG_BFS_DEFER
+            if (dq_valid) {
+                Q[dq_pos] = make_uint2(dq_a, dq_b - dq_a);
+                pos[dq_w] = dq_pos;
+                deg_acc += dq_b - dq_a;
+                dq_valid = false;
+            }
+#endif
             {                                               // adjacency entries of the next frontier
                 unsigned tot2;
                 block_scan_incl(deg_acc, s_tot + 32 * (flip ^= 1u), tot2);

@@ -12,6 +12,8 @@
 //   3. softmax (utils.py:131-133) + float64 CDF + inverse-CDF draw (numpy legacy
 //      RandomState.choice, called at graph_gan.py:262) with warp shuffles.
 // The arithmetic is the canonical sequence of DESIGN.md section 3 == oracle/gg_oracle.c.
+#include <string.h>
+
 #include "walk_common.cuh"
 
 namespace gg {
@@ -194,19 +196,31 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t
 // a (root, depth-1 child) pair gets a shared CDF (step1_cdf_kernel) when at least this many walks picked it
 constexpr int S1_MIN_WALKS = 2;
 
+// where a walk (re)starts: a fresh walk stands on its root; a walk handed over by the level-synchronous steps
+// (flat_*_kernel below) continues from the node it reached (step == choices made so far)
+struct WalkState {
+    int cur, prev, step, fedge, suml;
+};
+
 template <int CPL>
 __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slot, uint32_t k, long long w,
                                         int *s_ids, float *s_sc, int *g_ids, float *g_sc, int lane,
                                         unsigned long long &raw_steps, unsigned long long &raw_suml,
                                         unsigned long long &overflow, unsigned long long &rows_gathered,
-                                        unsigned int (&cyc)[7], Stage &stg) {
+                                        unsigned int (&cyc)[7], Stage &stg, const WalkState *from = nullptr) {
     const int root = d.roots[slot];
     const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
     int cur = root, prev = -1, step = 0, fedge = -1, plen = 0;
     int steps = 0, suml = 0, status = GG_NOTRUN, sample = -1;
     int32_t *prow = (d.max_path > 0 && d.paths) ? d.paths + (size_t)w * (size_t)d.max_path : nullptr;
-    if (prow && lane == 0) prow[0] = cur;
-    plen = 1;
+    if (from) {
+        cur = from->cur; prev = from->prev; step = from->step; fedge = from->fedge; steps = from->step; suml = from->suml;
+        plen = step + 1;
+    } else {
+        if (prow && lane == 0) prow[0] = cur;
+        plen = 1;
+    }
+    const int steps_in = steps, suml_in = suml;
 
     const long long t_walk = clock64();
     for (;;) {
@@ -266,7 +280,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
         prev = cur; cur = nxt; ++step;
     }
     cyc[6] += (unsigned int)(clock64() - t_walk);
-    raw_steps += (unsigned)steps; raw_suml += (unsigned)suml;
+    raw_steps += (unsigned)(steps - steps_in); raw_suml += (unsigned)(suml - suml_in);
     if (lane == 0) {
         d.samples[w] = sample;
         d.status[w] = status;
@@ -376,8 +390,25 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) step1_cdf_k
 }
 
 // ---------------------------------------------------------------- order-free (Philox) kernel
+// FlatView: the buffers of the level-synchronous steps (see below), carved out of gg_walk_desc.flat_buf.
+struct FlatView {
+    int *cur, *prev;       // [W] node a handed-over walk stands on / came from
+    int *list[2];          // [W] walks that execute step s next: list[s & 1]
+    int *tail;             // [W] walks the persistent kernel finishes (after the last level-synchronous step)
+    int *hub;              // [W] per level: items (indices into the level's list) that stand on a score-cached node
+    int *item_n;           // [W] per item: candidate-list length | father flag << 30 (0: nothing left to do for the item)
+    int *pool_ids;         // [W * stride] per item: its candidate ids
+    unsigned *ctr;         // counters: [0] tail length; level s: [1 + 4 s + {0: items, 1: hub items, 2: -, 3: work queue}]
+    int stride;            // pool entries per item (>= hub_threshold: a node below the threshold has fewer neighbours)
+    int steps;             // level-synchronous steps 1 .. steps
+};
+constexpr int FLAT_MAX_STEPS = 14;
+constexpr int FLAT_CTR_WORDS = 1 + 4 * (FLAT_MAX_STEPS + 2);
+#define GG_FCTR(fv, s, k) ((fv).ctr + 1 + 4 * (s) + (k))
+
 template <int CPL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) walk_kernel(const __grid_constant__ gg_walk_desc d) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) walk_kernel(const __grid_constant__ gg_walk_desc d,
+                                                                                 const FlatView fv, const int tail_mode) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
@@ -404,11 +435,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) walk_kernel
     unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
     const bool ratio_all = d.update_ratio >= 1.0;
 
+    const long long n_items = tail_mode ? (long long)fv.ctr[0] : d.n_walks;
     for (;;) {
         unsigned int wi = 0;
         if (lane == 0) wi = atomicAdd(d.work_counter, 1u);
         wi = __shfl_sync(FULL, wi, 0);
-        if ((long long)wi >= d.n_walks) break;
+        if ((long long)wi >= n_items) break;
+        if (tail_mode) {
+            // a walk handed over by the level-synchronous steps: continue where it stands
+            const long long w = fv.tail[wi];
+            const int slot = __ldg(d.walk_slot + w);
+            WalkState from;
+            from.cur = fv.cur[w]; from.prev = fv.prev[w]; from.step = d.wsteps[w]; from.fedge = d.first_edge[w]; from.suml = d.wsuml[w];
+            walk_one<CPL>(d, rng, slot, (uint32_t)(w - __ldg(d.walk_ptr + slot)), w, s_ids, s_sc, g_ids, g_sc, lane, raw_steps,
+                          raw_suml, overflow, rows_gathered, cyc, stg, &from);
+            continue;
+        }
         const long long w = d.walk_order ? (long long)__ldg(d.walk_order + wi) : (long long)wi;
         // walk -> root slot: last slot with walk_ptr[slot] <= w (table when the caller provides one)
         int slot;
@@ -445,6 +487,277 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) walk_kernel
         if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
         if (rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
     }
+}
+
+// ---------------------------------------------------------------- level-synchronous ("flat") steps
+// The persistent kernel above gives every walk to one warp from root to leaf: per step the warp runs the dependent chain
+// indptr -> tree bits / adjacency -> embedding rows -> softmax -> draw alone, so most of the time a resident warp has
+// nothing in flight (ncu: 22 cycles per issued instruction, a third of them instruction-cache misses of 32 warps
+// scattered over 130 KB of code).  Here all unfinished walks take step s TOGETHER, one phase per kernel:
+//   flat_start_kernel   thread per walk: the root step (inverts the root's CDF) and, for (root, child) pairs picked by
+//                       several walks, step 1 from the shared CDF (step1_cdf_kernel); survivors enter level 1 or 2
+//   flat_enum_kernel    warp per unfinished walk: candidate list [father] + children(cur) from the tree bits into the
+//                       item's slab of the id pool (short chain: indptr -> bits + adjacency); empty and single-candidate
+//                       lists are finished on the spot; walks standing on a score-cached (hub) node go to the hub list
+//   flat_choose_kernel  warp per item: on-demand scores (rows of the candidates: the only phase with row gathers, so
+//                       every resident warp has 8 rows in flight almost all the time), softmax + CDF + draw, next
+//                       node; hub items run the cached-list step of the persistent kernel (TMA-staged enumeration)
+// and after `steps` levels the few walks still alive are finished by walk_kernel in tail mode.  Same arithmetic, same
+// Philox counters (root, walk, step): bit-identical to the persistent kernel (tests: test_flat_steps_*).
+__device__ __forceinline__ bool step_includes_father(const gg_walk_desc &d, int s, int fedge) {
+    if (s == 0) return false;                              // graph_gan.py:250: the root has no father
+    if (s == 1) {
+        if (d.for_d) return false;                         // graph_gan.py:255-257
+        return !((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u);   // graph_gan.py:258-259: father entry removed by a D pass
+    }
+    return true;
+}
+
+// lane 0: the walk made its choice at step s over n candidates
+__device__ __forceinline__ void flat_advance(const gg_walk_desc &d, const FlatView &fv, int s, long long w, int cur, int n,
+                                             int idx, int nxt, bool inc_father, unsigned long long &overflow) {
+    if (d.max_path > 0 && d.paths && s + 1 < d.max_path) d.paths[(size_t)w * (size_t)d.max_path + s + 1] = nxt;
+    d.wsteps[w] = s + 1;
+    d.wsuml[w] = d.wsuml[w] + n;
+    if (inc_father && idx == 0) {                          // graph_gan.py:264-266: back to the father: cur is the sample
+        d.samples[w] = cur; d.status[w] = GG_DONE;
+        if (d.path_len) d.path_len[w] = s + 2;
+        if (d.max_path > 0 && s + 2 > d.max_path) overflow += 1;
+    } else {
+        fv.cur[w] = nxt; fv.prev[w] = cur;
+        if (s < fv.steps) fv.list[(s + 1) & 1][atomicAdd(GG_FCTR(fv, s + 1, 0), 1u)] = (int)w;
+        else fv.tail[atomicAdd(fv.ctr, 1u)] = (int)w;
+    }
+}
+__device__ __forceinline__ void flat_void(const gg_walk_desc &d, int s, long long w) {   // lane 0; graph_gan.py:252-257
+    d.samples[w] = -1; d.status[w] = GG_VOID; d.wsteps[w] = s;
+    if (d.path_len) d.path_len[w] = 0;
+}
+
+__global__ void __launch_bounds__(256) flat_start_kernel(const __grid_constant__ gg_walk_desc d, const FlatView fv) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int dest = 0;                                          // 1 / 2: enters level 1 / 2 (or the tail when there is no such level)
+    unsigned steps = 0, suml = 0, over = 0;
+    if (w < d.n_walks) {
+        const int slot = __ldg(d.walk_slot + w);
+        const int root = d.roots[slot];
+        const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
+        const int fi = d.first_idx[w];                      // root_step_kernel: -2 skipped (update_ratio), -1 isolated root
+        int32_t *prow = (d.max_path > 0 && d.paths) ? d.paths + (size_t)w * (size_t)d.max_path : nullptr;
+        int sample = -1, status = GG_NOTRUN, fedge = -1, ws = 0, wl = 0, plen = 0;
+        if (fi == -2) {
+            status = GG_SKIPPED;
+        } else {
+            if (prow) prow[0] = root;
+            if (fi < 0) {
+                status = GG_VOID;                           // graph_gan.py:252-253
+            } else {
+                const long long a0 = d.indptr[root];
+                const int n0 = (int)(d.indptr[root + 1] - a0);
+                fedge = (int)(a0 + fi);
+                const int c = __ldg(d.adj + fedge);
+                if (prow && 1 < d.max_path) prow[1] = c;
+                ws = 1; wl = n0; steps = 1; suml = (unsigned)n0;
+                const long long s1pos = __ldg(d.rq_ptr + slot) + fi;
+                if (__ldg(d.s1_cnt + s1pos) >= S1_MIN_WALKS) {
+                    const int n = __ldg(d.s1_n + s1pos);
+                    if (n == 0) {
+                        status = GG_VOID;                   // graph_gan.py:255-257
+                    } else {
+                        const bool inc_father = step_includes_father(d, 1, fedge);
+                        uint32_t a, b;
+                        philox4x32_10((uint32_t)root, k, 1u, d.pass_tag, (uint32_t)d.seed, (uint32_t)(d.seed >> 32), a, b);
+                        const long long o = __ldg(d.s1_ptr + s1pos);
+                        const int idx = (n == 1) ? 0 : cdf_search_raw(d.s1_q + o, n, u53(a, b));
+                        const int nxt = __ldg(d.s1_ids + o + idx);
+                        if (prow && 2 < d.max_path) prow[2] = nxt;
+                        ws = 2; wl = n0 + n; steps = 2; suml = (unsigned)(n0 + n);
+                        if (inc_father && idx == 0) {
+                            sample = c; status = GG_DONE; plen = 3;
+                            if (d.max_path > 0 && 3 > d.max_path) over = 1;
+                        } else {
+                            fv.cur[w] = nxt; fv.prev[w] = c; dest = 2;
+                        }
+                    }
+                } else {
+                    fv.cur[w] = c; fv.prev[w] = root; dest = 1;
+                }
+            }
+        }
+        d.samples[w] = sample; d.status[w] = status; d.first_edge[w] = fedge; d.wsteps[w] = ws; d.wsuml[w] = wl;
+        if (d.path_len) d.path_len[w] = plen;
+    }
+    // warp-aggregated appends (one atomic per warp and destination)
+#pragma unroll
+    for (int lv = 1; lv <= 2; ++lv) {
+        const unsigned mk = __ballot_sync(FULL, dest == lv);
+        if (!mk) continue;
+        const int leader = __ffs(mk) - 1;
+        int *list = (lv <= fv.steps) ? fv.list[lv & 1] : fv.tail;
+        unsigned *cnt = (lv <= fv.steps) ? GG_FCTR(fv, lv, 0) : fv.ctr;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(cnt, (unsigned)__popc(mk));
+        base = __shfl_sync(FULL, base, leader);
+        if (dest == lv) list[base + __popc(mk & ((1u << lane) - 1u))] = (int)w;
+    }
+    steps = __reduce_add_sync(FULL, steps); suml = __reduce_add_sync(FULL, suml); over = __reduce_add_sync(FULL, over);
+    if (lane == 0) {
+        if (steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, (unsigned long long)steps);
+        if (suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, (unsigned long long)suml);
+        if (over) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, (unsigned long long)over);
+    }
+}
+
+constexpr int FLAT_ENUM_WARPS = 8;
+__global__ void __launch_bounds__(FLAT_ENUM_WARPS * 32, 8) flat_enum_kernel(const __grid_constant__ gg_walk_desc d,
+                                                                            const FlatView fv, const int s) {
+    const int lane = threadIdx.x & 31;
+    const unsigned gw = blockIdx.x * FLAT_ENUM_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * FLAT_ENUM_WARPS;
+    const int *A = fv.list[s & 1];
+    const unsigned nA = *GG_FCTR(fv, s, 0);
+    Stage stg;
+    stg.buf = nullptr; stg.bar = nullptr; stg.phase = 0u; stg.on = false;
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0;
+    for (unsigned i = gw; i < nA; i += nwarps) {
+        const long long w = A[i];
+        const int cur = fv.cur[w], prev = fv.prev[w];
+        const long long a0 = d.indptr[cur], a1 = d.indptr[cur + 1];
+        if (d.edge_score && (a1 - a0) >= d.hub_threshold) {          // score-cached node: the whole step runs in flat_choose_kernel
+            if (lane == 0) { fv.hub[atomicAdd(GG_FCTR(fv, s, 1), 1u)] = (int)i; fv.item_n[i] = 0; }
+            continue;
+        }
+        const int slot = __ldg(d.walk_slot + w);
+        const bool inc_father = step_includes_father(d, s, s == 1 ? d.first_edge[w] : 0);
+        const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
+        int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
+        int n = 0;
+        if (inc_father) { if (lane == 0) ids[0] = prev; n = 1; }
+        float m = 0.0f;
+        enumerate_children<UNR>(d, tb, a0, a1, false, ids, nullptr, lane, n, m, stg);
+        __syncwarp();
+        if (n == 0) {
+            if (lane == 0) { flat_void(d, s, w); fv.item_n[i] = 0; }
+        } else if (n == 1) {
+            // softmax = [1.0], cdf = [1.0] and 1.0 > u for every u in [0, 1): index 0, no score, no draw needed
+            const int nxt = inc_father ? prev : ids[0];
+            if (lane == 0) { flat_advance(d, fv, s, w, cur, 1, 0, nxt, inc_father, overflow); fv.item_n[i] = 0; }
+            raw_steps += 1; raw_suml += 1;
+        } else if (lane == 0) {
+            fv.item_n[i] = n | (inc_father ? (1 << 30) : 0);
+        }
+    }
+    if (lane == 0) {
+        if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
+        if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
+        if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
+    }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose_kernel(const __grid_constant__ gg_walk_desc d,
+                                                                                        const FlatView fv, const int s) {
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * WALK_SMEM_PER_WARP);
+    int *s_ids = reinterpret_cast<int *>(s_sc + SC_CAP);
+    Stage stg;
+    stg.buf = s_sc;
+    stg.bar = reinterpret_cast<unsigned long long *>(s_ids + ID_CAP);
+    stg.phase = 0u;
+    stg.on = !d.no_tma && d.edge_score != nullptr;
+    if (stg.on) {
+        if (lane == 0) {
+            mbar_init(stg.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
+    int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
+    float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
+    const int *A = fv.list[s & 1];
+    const unsigned nA = *GG_FCTR(fv, s, 0), nH = *GG_FCTR(fv, s, 1);
+    const uint32_t k0 = (uint32_t)d.seed, k1 = (uint32_t)(d.seed >> 32);
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
+    unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (;;) {
+        unsigned j = 0;
+        if (lane == 0) j = atomicAdd(GG_FCTR(fv, s, 3), 1u);
+        j = __shfl_sync(FULL, j, 0);
+        if (j >= nH + nA) break;
+        const bool hub_item = j < nH;                       // the hub items first: they are the long ones
+        const unsigned i = hub_item ? (unsigned)fv.hub[j] : j - nH;
+        int rec = 0;
+        if (!hub_item) {
+            rec = fv.item_n[i];
+            if ((rec & 0x3fffffff) < 2) continue;           // finished by flat_enum_kernel, or a hub item
+        }
+        const long long w = A[i];
+        const int cur = fv.cur[w], prev = fv.prev[w];
+        const int slot = __ldg(d.walk_slot + w);
+        const int root = d.roots[slot];
+        const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
+        int n, idx, nxt;
+        bool inc_father;
+        uint32_t a, b;
+        if (hub_item) {
+            inc_father = step_includes_father(d, s, s == 1 ? d.first_edge[w] : 0);
+            const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
+            int *ids; float *sc; float m;
+            build_list<CPL, UNR>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
+            if (n == 0) {
+                if (lane == 0) flat_void(d, s, w);
+                continue;
+            }
+            philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
+            idx = (n == 1) ? 0 : choose_index(sc, n, m, u53(a, b), lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
+            nxt = ids[idx];
+            __syncwarp();
+        } else {
+            n = rec & 0x3fffffff;
+            inc_father = (rec >> 30) & 1;
+            const int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
+            float4 c4[CPL];
+            load_row<CPL>(d.emb, d.ld, cur, lane & 7, c4);
+            score_list<CPL>(d.emb, d.bias, d.ld, c4, ids, s_sc, n, cur, lane);
+            rows_gathered += 1u + (unsigned)n;
+            const float m = list_max(s_sc, n, lane);
+            philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
+            idx = choose_index(s_sc, n, m, u53(a, b), lane);
+            nxt = ids[idx];
+            __syncwarp();
+        }
+        if (lane == 0) flat_advance(d, fv, s, w, cur, n, idx, nxt, inc_father, overflow);
+        raw_steps += 1; raw_suml += (unsigned)n;
+    }
+    if (lane == 0) {
+        if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
+        if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
+        if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
+        if (rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
+    }
+}
+
+// the layout of desc.flat_buf (host): returns the bytes needed; fills `fv` when `buf` is given
+size_t flat_layout(void *buf, long long n_walks, int hub_threshold, int steps, FlatView *fv) {
+    const size_t W = (size_t)(n_walks > 0 ? n_walks : 1);
+    const int stride = ((hub_threshold > 0 ? hub_threshold : 1) + 31) / 32 * 32;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void *p = buf ? (void *)((unsigned char *)buf + off) : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    unsigned *ctr = (unsigned *)take(sizeof(unsigned) * FLAT_CTR_WORDS);
+    int *cur = (int *)take(4 * W), *prev = (int *)take(4 * W), *l0 = (int *)take(4 * W), *l1 = (int *)take(4 * W);
+    int *tail = (int *)take(4 * W), *hub = (int *)take(4 * W), *item_n = (int *)take(4 * W);
+    int *pool = (int *)take(4 * W * (size_t)stride);
+    if (fv) {
+        fv->ctr = ctr; fv->cur = cur; fv->prev = prev; fv->list[0] = l0; fv->list[1] = l1; fv->tail = tail; fv->hub = hub;
+        fv->item_n = item_n; fv->pool_ids = pool; fv->stride = stride; fv->steps = steps;
+    }
+    return off;
 }
 
 // ---------------------------------------------------------------- reference-order (stream) kernel
@@ -590,6 +903,12 @@ extern "C" int gg_walk_scratch_bytes(int32_t max_cand, int64_t *bytes) {
     return 0;
 }
 
+extern "C" int gg_walk_flat_bytes(int64_t n_walks, int32_t hub_threshold, int32_t flat_steps, int64_t *bytes) {
+    GG_REQUIRE(bytes && n_walks >= 0 && hub_threshold > 0 && flat_steps >= 0 && flat_steps <= gg::FLAT_MAX_STEPS, "bad arguments");
+    *bytes = (int64_t)gg::flat_layout(nullptr, n_walks, hub_threshold, flat_steps, nullptr);
+    return 0;
+}
+
 extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
     GG_REQUIRE(dp, "null descriptor");
     const gg_walk_desc &d = *dp;
@@ -661,11 +980,44 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
             GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));   // the walk kernel's queue starts at 0
         }
         if (!(pm & 2)) return 0;
+        gg::FlatView fv;
+        memset(&fv, 0, sizeof(fv));
+        int tail_mode = 0;
+        if (d.flat_steps > 0) {
+            // level-synchronous steps (flat_*_kernel), then the persistent kernel finishes what is left
+            GG_REQUIRE(d.s1_q && d.edge_score && d.root_q && d.walk_slot && d.first_idx, "flat_steps needs the depth-1 reuse (s1_*, edge_score, root_q, walk_slot)");
+            GG_REQUIRE(d.flat_steps <= gg::FLAT_MAX_STEPS, "flat_steps too large");
+            GG_REQUIRE(d.flat_buf && d.flat_bytes >= (int64_t)gg::flat_layout(nullptr, d.n_walks, d.hub_threshold, d.flat_steps, nullptr),
+                       "flat_buf too small (gg_walk_flat_bytes)");
+            gg::flat_layout(d.flat_buf, d.n_walks, d.hub_threshold, d.flat_steps, &fv);
+            GG_CHECK(cudaMemsetAsync(fv.ctr, 0, sizeof(unsigned) * gg::FLAT_CTR_WORDS, st));
+            gg::flat_start_kernel<<<(unsigned)((d.n_walks + 255) / 256), 256, 0, st>>>(d, fv);
+            GG_CHECK(cudaGetLastError());
+            const int enum_ctas = gg::sm_count() * 8;
+            for (int s = 1; s <= d.flat_steps; ++s) {
+                gg::flat_enum_kernel<<<enum_ctas, gg::FLAT_ENUM_WARPS * 32, 0, st>>>(d, fv, s);
+                GG_CHECK(cudaGetLastError());
+                switch (cpl) {
+#define GG_FLAT(C)                                                                                                    \
+    GG_CHECK(cudaFuncSetAttribute(gg::flat_choose_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                  gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                      \
+    gg::flat_choose_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d, fv, s)
+                    case 1: GG_FLAT(1); break;
+                    case 2: GG_FLAT(2); break;
+                    case 4: GG_FLAT(4); break;
+                    case 8: GG_FLAT(8); break;
+#undef GG_FLAT
+                    default: gg::set_error("gg_walk_sample: unsupported ld %d (supported: 32, 64, 128, 256)", d.ld); return 2;
+                }
+                GG_CHECK(cudaGetLastError());
+            }
+            tail_mode = 1;
+        }
         switch (cpl) {
 #define GG_WALK(C)                                                                                                    \
     GG_CHECK(cudaFuncSetAttribute(gg::walk_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
                                   gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                      \
-    gg::walk_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d)
+    gg::walk_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d, fv, tail_mode)
             case 1: GG_WALK(1); break;
             case 2: GG_WALK(2); break;
             case 4: GG_WALK(4); break;

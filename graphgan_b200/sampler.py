@@ -142,6 +142,17 @@ class WalkPlan:
             self._order = (base + torch.arange(self.n_walks, dtype=torch.int64, device=dev)).to(torch.int32)
         return self._order
 
+    def flat_buffer(self, sampler):
+        """scratch of the level-synchronous steps (csrc/walk.cu: flat_*_kernel), sized by the library"""
+        key = (sampler.flat_steps, sampler.hub_threshold)
+        if getattr(self, "_flat_key", None) != key:
+            nbytes = C.c_int64(0)
+            _cabi.check(sampler.lib.gg_walk_flat_bytes(self.n_walks, sampler.hub_threshold, sampler.flat_steps, C.byref(nbytes)),
+                        "gg_walk_flat_bytes")
+            self._flat = sampler.torch.empty(max(nbytes.value, 16), dtype=sampler.torch.uint8, device=sampler.device)
+            self._flat_key = key
+        return self._flat
+
     def depth1_buffers(self, sampler):
         """Static layout of the depth-1 CDF cache (csrc/walk.cu: step1_cdf_kernel): one slice of degree(child) + 1
         entries per (root, neighbour) pair.  Built on first use (plumbing: gathers + one cumsum)."""
@@ -186,6 +197,8 @@ class WalkSampler:
         # bottom-up levels only; the trees are identical in every mode (tests/test_walk_gpu.py)
         self.bfs_bottom_up_ratio = float(os.environ.get("GG_BFS_BU_RATIO", "-1"))
         self.bfs_flags = 0
+        # level-synchronous walk steps (csrc/walk.cu: flat_*_kernel) for steps 1..flat_steps; 0 = persistent kernel only
+        self.flat_steps = int(os.environ.get("GG_FLAT_STEPS", "0"))
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -245,6 +258,9 @@ class WalkSampler:
                 d.s1_q, d.s1_ids, d.first_idx = ptr(b["q"]), ptr(b["ids"]), ptr(b["first"])
                 if self.hub_first:
                     d.s1_order = ptr(b["order"])
+                if self.flat_steps > 0:
+                    buf = plan.flat_buffer(self)
+                    d.flat_buf, d.flat_bytes, d.flat_steps = ptr(buf), buf.numel(), self.flat_steps
         return d
 
     def precompute(self, emb, bias, plan, desc=None):

@@ -127,6 +127,13 @@ typedef struct gg_walk_desc {
                                  * step1_cdf_kernel pulls pairs from a queue (largest lists first) instead of striding */
     const int32_t *walk_order;  /* optional device [W]: the order in which walk_kernel starts the walks (a permutation of
                                  * 0..W-1, e.g. expensive roots first); results do not depend on it (Philox mode) */
+    /* optional level-synchronous steps (needs the depth-1 reuse): all unfinished walks take step s together -- one
+       kernel enumerates the candidate lists, one gathers the candidates' rows and draws -- for steps 1..flat_steps;
+       the persistent kernel finishes the walks that are still alive after that.  Identical results. */
+    void *flat_buf;             /* device scratch of gg_walk_flat_bytes(n_walks, hub_threshold, flat_steps) bytes */
+    int64_t flat_bytes;
+    int32_t flat_steps;         /* 0 = off (persistent kernel only); <= 14 */
+    int32_t flat_reserved;
 } gg_walk_desc;
 
 /* all_score[u, v] = e_u.e_v + b_v (generator.py:21) for every walk-CSR entry (u -> v) of the listed hub
@@ -141,6 +148,7 @@ int gg_hub_scores(int64_t n_tiles, const int32_t *tile_node, const int64_t *tile
 int gg_root_cdf(const gg_walk_desc *d, float *root_sc, double *root_q, void *stream);
 
 int gg_walk_scratch_bytes(int32_t max_cand, int64_t *bytes);
+int gg_walk_flat_bytes(int64_t n_walks, int32_t hub_threshold, int32_t flat_steps, int64_t *bytes);
 int gg_walk_sample(const gg_walk_desc *d, void *stream);
 
 /* Per root: find the first voiding walk (graph_gan.py:252-257 returns None for the WHOLE

@@ -20,13 +20,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _compare(hg, emb_h, roots, sample_cap, n_sample_gen, cuda_device, hub_threshold=128, max_path=64, seed=11, bias_h=None):
+def _compare(hg, emb_h, roots, sample_cap, n_sample_gen, cuda_device, hub_threshold=128, max_path=64, seed=11, bias_h=None,
+             flat_steps=0):
     import torch
     from graphgan_b200 import graph as G, sampler as S
     from oracle import canonical as can
     roots = np.asarray(roots, np.int32)
     dg = G.DeviceGraph(hg, cuda_device)
     smp = S.WalkSampler(dg, hub_threshold=hub_threshold)
+    smp.flat_steps = flat_steps       # 0: persistent walk kernel; > 0: level-synchronous steps first (csrc/walk.cu: flat_*_kernel)
     trees = smp.build_trees(roots)
     par = trees.parent_arrays().cpu().numpy()
     want = can.bfs_parents(hg.indptr, hg.adj, roots)
@@ -67,7 +69,8 @@ def _compare(hg, emb_h, roots, sample_cap, n_sample_gen, cuda_device, hub_thresh
     return stats
 
 
-def test_c3_powerlaw_1m_with_hub_roots(cuda_device):
+@pytest.mark.parametrize("flat_steps", [0, 4])
+def test_c3_powerlaw_1m_with_hub_roots(flat_steps, cuda_device):
     """BASELINE.json configs[2]: the graph bench.py times.  Roots: the top-degree node, three of its neighbours, other
     hubs, and a spread of ordinary roots."""
     from graphgan_b200 import graph as G, synth
@@ -81,23 +84,26 @@ def test_c3_powerlaw_1m_with_hub_roots(cuda_device):
     ordinary = rs.choice(np.flatnonzero(hg.degrees() > 0), 56, replace=False)
     roots = np.unique(np.concatenate([[top, 1, 7, 300], nb[[0, len(nb) // 2, len(nb) - 1]], ordinary]))
     emb_h = synth.embeddings(n, d, seed=1)
-    st = _compare(hg, emb_h, roots, sample_cap=40, n_sample_gen=20, cuda_device=cuda_device)
+    st = _compare(hg, emb_h, roots, sample_cap=40, n_sample_gen=20, cuda_device=cuda_device, flat_steps=flat_steps)
     assert st["d"]["max_l"] > 2048          # candidate lists longer than the shared-memory score buffer were walked
     assert st["g"]["overflow"] == 0
 
 
-def test_c2_erdos_renyi_100k(cuda_device):
+@pytest.mark.parametrize("flat_steps", [0, 1, 3])
+def test_c2_erdos_renyi_100k(flat_steps, cuda_device):
     """BASELINE.json configs[1]: ER N = 100k, avg-deg 10, n_emb = 128; 256 roots with their full sample_num."""
     from graphgan_b200 import graph as G, synth
     n, d = 100_000, 128
     hg = G.HostGraph(synth.erdos_renyi(n, 10, seed=0), None, n_node=n)
     roots = synth.pick_roots(hg.degrees(), 256, seed=0)
-    st = _compare(hg, synth.embeddings(n, d, seed=1), roots, sample_cap=1 << 30, n_sample_gen=20, cuda_device=cuda_device)
+    st = _compare(hg, synth.embeddings(n, d, seed=1), roots, sample_cap=1 << 30, n_sample_gen=20, cuda_device=cuda_device,
+                  flat_steps=flat_steps)
     assert st["d"]["walks"] == int(hg.degrees()[roots].sum())
     assert st["g"]["overflow"] == 0
 
 
-def test_c5_shape_deep_trees_ld256(cuda_device):
+@pytest.mark.parametrize("flat_steps", [0, 14])
+def test_c5_shape_deep_trees_ld256(flat_steps, cuda_device):
     """BASELINE.json configs[4] shape: avg-deg 8, n_emb = 256, deep BFS trees.  N = 2M (the tree builder's visited
     bitmap no longer fits in shared memory) plus a 44-node path hanging off a low-degree node, and roots at and next to
     the path's far end: BFS depth > 40.  The generator's biases grow by 8 per node towards the anchor, so walks that
@@ -116,6 +122,6 @@ def test_c5_shape_deep_trees_ld256(cuda_device):
     bias_h = np.random.RandomState(5).normal(0, 0.1, n).astype(np.float32)
     bias_h[n0:] = 8.0 * (tail - 1 - np.arange(tail))
     st = _compare(hg, synth.embeddings(n, d, seed=6, sigma=0.35), roots, sample_cap=48, n_sample_gen=20,
-                  cuda_device=cuda_device, bias_h=bias_h)
+                  cuda_device=cuda_device, bias_h=bias_h, flat_steps=flat_steps)
     assert st["g"]["overflow"] == 0 and st["d"]["overflow"] == 0
     assert 40 < st["g"]["max_path"] <= 64                  # deep walks really occurred, and fit
