@@ -601,8 +601,18 @@ def run_b200(args):
         root_rows = int(deg_w[deg_w < smp.hub_threshold].sum() + len(roots)) if reuse else 0
         all_rows = float(np.mean([c["rows_gathered"] for c in cnts])) + hub_edges + root_rows     # whole K1 stage
         key = "%s@R%d" % (args.workload, args.roots)
-        traffic, traffic_src = _ncu_traffic("walk_kernel", key)
+        flat = smp.flat_steps if (reuse and smp.depth1) else 0
+        traffic, traffic_src = _ncu_traffic("walk_stage" if flat else "walk_kernel", key)
         stage_traffic, _ = _ncu_traffic("k1_stage", key)
+        choose_us, _ = _ncu_traffic("flat_choose_kernel_ncu_us_per_pass", key)
+        stage_us, _ = _ncu_traffic("walk_stage_ncu_us", key)
+        if flat:
+            kname = ("walk stage = gg::flat_start_kernel + %d x (gg::flat_enum_kernel + gg::flat_choose_kernel<%d>) + gg::walk_kernel<%d> "
+                     "tail (dominant stage: %.0f %% of the K1 stage%s)" % (
+                         flat, ld // 32, ld // 32, 100 * walk_ms / k1_ms,
+                         "; flat_choose_kernel = %.0f %% of it in the ncu launch list" % (100 * choose_us / stage_us) if choose_us and stage_us else ""))
+        else:
+            kname = "gg::walk_kernel<%d> (dominant: %.0f %% of the K1 stage)" % (ld // 32, 100 * walk_ms / k1_ms)
         useful = brows * row_b                                       # embedding rows + bias + id the dominant kernel gathered
         achieved = useful / (walk_ms * 1e-3) / 1e9
         line = {
@@ -617,9 +627,9 @@ def run_b200(args):
                     "call": "WalkSampler.precompute + run + finalize + emit_d_rows with pinned host roots in / rows out",
                     "note": "trees and the walk plan of these roots are resident (SURVEY 8d); a NEW root batch also costs "
                             "gg_bfs_build + the plan -- see full_pass"},
-            "gpu_launches": ((9 if smp.depth1 else 7) if reuse else 5) * args.steps,
+            "gpu_launches": (((9 if smp.depth1 else 7) if reuse else 5) + ((1 + 2 * flat) if flat else 0)) * args.steps,
             "parity": parity,
-            "roofline": {"bound": "hbm", "kernel": "gg::walk_kernel<%d> (dominant: %.0f %% of the K1 stage)" % (ld // 32, 100 * walk_ms / k1_ms),
+            "roofline": {"bound": "hbm", "kernel": kname, "flat_steps": flat,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel_ms": walk_ms,
@@ -634,11 +644,12 @@ def run_b200(args):
                          "survey_algorithmic_bytes_per_launch": survey_bytes,
                          "algorithmic_reuse_ratio": survey_bytes / max(all_rows * row_b, 1.0),
                          "bytes_per_neg_edge_survey": survey_bytes / max(c0["accepted"], 1),
-                         "note": "achieved = (embedding row + bias + id) bytes the walk kernel gathers on demand per launch / its "
-                                 "event-timed duration (frac = useful_frac); dram_frac uses ncu dram__bytes of the same kernel when "
-                                 "a capture of THESE sources is committed.  The kernel is latency-bound (dependent chain indptr -> "
-                                 "tree bits -> adj -> rows), not bandwidth-bound.  SURVEY 8d's formula counts every candidate row at "
-                                 "every visit; the kernels fetch algorithmic_reuse_ratio x fewer bytes (exact reuse, DESIGN.md 5)"},
+                         "note": "achieved = (embedding row + bias + id) bytes the walk stage gathers on demand per pass / its "
+                                 "event-timed duration (frac = useful_frac); dram_frac uses ncu dram__bytes of the same kernels when "
+                                 "a capture of THESE sources is committed.  With flat_steps > 0 the stage is a sequence of "
+                                 "level-synchronous kernels (the row gathers sit in flat_choose_kernel) and is timed as a whole.  "
+                                 "SURVEY 8d's formula counts every candidate row at every visit; the kernels fetch "
+                                 "algorithmic_reuse_ratio x fewer bytes (exact reuse, DESIGN.md 5)"},
             "rates": {"walks_per_s": float(tot[3] / (tmax[0] * 1e-3)), "walk_steps_per_s": float(tot[2] / (tmax[0] * 1e-3)),
                       "g_mode": g_stats},
             "full_pass": {"neg_edges_per_s": c0["accepted"] / ((tmax[2] + plan_ms + tmax[0] / args.steps) * 1e-3),

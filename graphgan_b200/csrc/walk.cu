@@ -392,9 +392,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) step1_cdf_k
 // ---------------------------------------------------------------- order-free (Philox) kernel
 // FlatView: the buffers of the level-synchronous steps (see below), carved out of gg_walk_desc.flat_buf.
 struct FlatView {
-    int *cur, *prev;       // [W] node a handed-over walk stands on / came from
-    int *list[2];          // [W] walks that execute step s next: list[s & 1]
-    int *tail;             // [W] walks the persistent kernel finishes (after the last level-synchronous step)
+    int4 *list[2];         // [W] walks that execute step s next, as records (walk, node it stands on, node it came from,
+                           //     root slot): list[s & 1] -- one 16-byte load gives a kernel everything about the walk
+    int4 *tail;            // [W] walks the persistent kernel finishes (after the last level-synchronous step), same records
     int *hub;              // [W] per level: items (indices into the level's list) that stand on a score-cached node
     int *item_n;           // [W] per item: candidate-list length | father flag << 30 (0: nothing left to do for the item)
     int *pool_ids;         // [W * stride] per item: its candidate ids
@@ -443,10 +443,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) walk_kernel
         if ((long long)wi >= n_items) break;
         if (tail_mode) {
             // a walk handed over by the level-synchronous steps: continue where it stands
-            const long long w = fv.tail[wi];
-            const int slot = __ldg(d.walk_slot + w);
+            const int4 rec = fv.tail[wi];
+            const long long w = rec.x;
+            const int slot = rec.w;
             WalkState from;
-            from.cur = fv.cur[w]; from.prev = fv.prev[w]; from.step = d.wsteps[w]; from.fedge = d.first_edge[w]; from.suml = d.wsuml[w];
+            from.cur = rec.y; from.prev = rec.z; from.step = d.wsteps[w]; from.fedge = d.first_edge[w]; from.suml = d.wsuml[w];
             walk_one<CPL>(d, rng, slot, (uint32_t)(w - __ldg(d.walk_ptr + slot)), w, s_ids, s_sc, g_ids, g_sc, lane, raw_steps,
                           raw_suml, overflow, rows_gathered, cyc, stg, &from);
             continue;
@@ -514,8 +515,8 @@ __device__ __forceinline__ bool step_includes_father(const gg_walk_desc &d, int 
 }
 
 // lane 0: the walk made its choice at step s over n candidates
-__device__ __forceinline__ void flat_advance(const gg_walk_desc &d, const FlatView &fv, int s, long long w, int cur, int n,
-                                             int idx, int nxt, bool inc_father, unsigned long long &overflow) {
+__device__ __forceinline__ void flat_advance(const gg_walk_desc &d, const FlatView &fv, int s, long long w, int slot, int cur,
+                                             int n, int idx, int nxt, bool inc_father, unsigned long long &overflow) {
     if (d.max_path > 0 && d.paths && s + 1 < d.max_path) d.paths[(size_t)w * (size_t)d.max_path + s + 1] = nxt;
     d.wsteps[w] = s + 1;
     d.wsuml[w] = d.wsuml[w] + n;
@@ -524,9 +525,9 @@ __device__ __forceinline__ void flat_advance(const gg_walk_desc &d, const FlatVi
         if (d.path_len) d.path_len[w] = s + 2;
         if (d.max_path > 0 && s + 2 > d.max_path) overflow += 1;
     } else {
-        fv.cur[w] = nxt; fv.prev[w] = cur;
-        if (s < fv.steps) fv.list[(s + 1) & 1][atomicAdd(GG_FCTR(fv, s + 1, 0), 1u)] = (int)w;
-        else fv.tail[atomicAdd(fv.ctr, 1u)] = (int)w;
+        const int4 rec = make_int4((int)w, nxt, cur, slot);
+        if (s < fv.steps) fv.list[(s + 1) & 1][atomicAdd(GG_FCTR(fv, s + 1, 0), 1u)] = rec;
+        else fv.tail[atomicAdd(fv.ctr, 1u)] = rec;
     }
 }
 __device__ __forceinline__ void flat_void(const gg_walk_desc &d, int s, long long w) {   // lane 0; graph_gan.py:252-257
@@ -538,6 +539,7 @@ __global__ void __launch_bounds__(256) flat_start_kernel(const __grid_constant__
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int dest = 0;                                          // 1 / 2: enters level 1 / 2 (or the tail when there is no such level)
+    int4 rec = make_int4(0, 0, 0, 0);
     unsigned steps = 0, suml = 0, over = 0;
     if (w < d.n_walks) {
         const int slot = __ldg(d.walk_slot + w);
@@ -577,11 +579,11 @@ __global__ void __launch_bounds__(256) flat_start_kernel(const __grid_constant__
                             sample = c; status = GG_DONE; plen = 3;
                             if (d.max_path > 0 && 3 > d.max_path) over = 1;
                         } else {
-                            fv.cur[w] = nxt; fv.prev[w] = c; dest = 2;
+                            rec = make_int4((int)w, nxt, c, slot); dest = 2;
                         }
                     }
                 } else {
-                    fv.cur[w] = c; fv.prev[w] = root; dest = 1;
+                    rec = make_int4((int)w, c, root, slot); dest = 1;
                 }
             }
         }
@@ -594,12 +596,12 @@ __global__ void __launch_bounds__(256) flat_start_kernel(const __grid_constant__
         const unsigned mk = __ballot_sync(FULL, dest == lv);
         if (!mk) continue;
         const int leader = __ffs(mk) - 1;
-        int *list = (lv <= fv.steps) ? fv.list[lv & 1] : fv.tail;
+        int4 *list = (lv <= fv.steps) ? fv.list[lv & 1] : fv.tail;
         unsigned *cnt = (lv <= fv.steps) ? GG_FCTR(fv, lv, 0) : fv.ctr;
         unsigned base = 0;
         if (lane == leader) base = atomicAdd(cnt, (unsigned)__popc(mk));
         base = __shfl_sync(FULL, base, leader);
-        if (dest == lv) list[base + __popc(mk & ((1u << lane) - 1u))] = (int)w;
+        if (dest == lv) list[base + __popc(mk & ((1u << lane) - 1u))] = rec;
     }
     steps = __reduce_add_sync(FULL, steps); suml = __reduce_add_sync(FULL, suml); over = __reduce_add_sync(FULL, over);
     if (lane == 0) {
@@ -610,24 +612,26 @@ __global__ void __launch_bounds__(256) flat_start_kernel(const __grid_constant__
 }
 
 constexpr int FLAT_ENUM_WARPS = 8;
-__global__ void __launch_bounds__(FLAT_ENUM_WARPS * 32, 8) flat_enum_kernel(const __grid_constant__ gg_walk_desc d,
+__global__ void __launch_bounds__(FLAT_ENUM_WARPS * 32, 6) flat_enum_kernel(const __grid_constant__ gg_walk_desc d,
                                                                             const FlatView fv, const int s) {
     const int lane = threadIdx.x & 31;
     const unsigned gw = blockIdx.x * FLAT_ENUM_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * FLAT_ENUM_WARPS;
-    const int *A = fv.list[s & 1];
+    const int4 *A = fv.list[s & 1];
     const unsigned nA = *GG_FCTR(fv, s, 0);
     Stage stg;
     stg.buf = nullptr; stg.bar = nullptr; stg.phase = 0u; stg.on = false;
     unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0;
+    int4 rec_next = (gw < nA) ? A[gw] : make_int4(0, 0, 0, 0);
     for (unsigned i = gw; i < nA; i += nwarps) {
-        const long long w = A[i];
-        const int cur = fv.cur[w], prev = fv.prev[w];
+        const int4 rec = rec_next;
+        if (i + nwarps < nA) rec_next = A[i + nwarps];     // the next item's record is in flight while this one is enumerated
+        const long long w = rec.x;
+        const int cur = rec.y, prev = rec.z, slot = rec.w;
         const long long a0 = d.indptr[cur], a1 = d.indptr[cur + 1];
         if (d.edge_score && (a1 - a0) >= d.hub_threshold) {          // score-cached node: the whole step runs in flat_choose_kernel
             if (lane == 0) { fv.hub[atomicAdd(GG_FCTR(fv, s, 1), 1u)] = (int)i; fv.item_n[i] = 0; }
             continue;
         }
-        const int slot = __ldg(d.walk_slot + w);
         const bool inc_father = step_includes_father(d, s, s == 1 ? d.first_edge[w] : 0);
         const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
         int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
@@ -641,7 +645,7 @@ __global__ void __launch_bounds__(FLAT_ENUM_WARPS * 32, 8) flat_enum_kernel(cons
         } else if (n == 1) {
             // softmax = [1.0], cdf = [1.0] and 1.0 > u for every u in [0, 1): index 0, no score, no draw needed
             const int nxt = inc_father ? prev : ids[0];
-            if (lane == 0) { flat_advance(d, fv, s, w, cur, 1, 0, nxt, inc_father, overflow); fv.item_n[i] = 0; }
+            if (lane == 0) { flat_advance(d, fv, s, w, slot, cur, 1, 0, nxt, inc_father, overflow); fv.item_n[i] = 0; }
             raw_steps += 1; raw_suml += 1;
         } else if (lane == 0) {
             fv.item_n[i] = n | (inc_father ? (1 << 30) : 0);
@@ -676,60 +680,68 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
     const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + wid;
     int *g_ids = reinterpret_cast<int *>(d.scratch) + (size_t)gw * 2 * (size_t)d.max_cand;
     float *g_sc = reinterpret_cast<float *>(g_ids + d.max_cand);
-    const int *A = fv.list[s & 1];
+    const int4 *A = fv.list[s & 1];
     const unsigned nA = *GG_FCTR(fv, s, 0), nH = *GG_FCTR(fv, s, 1);
     const uint32_t k0 = (uint32_t)d.seed, k1 = (uint32_t)(d.seed >> 32);
     unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
     unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
+    // work queue: the hub items first, one per pull (they are the long ones); then the other items in chunks of
+    // FLAT_CHUNK consecutive list positions per pull, the next item's record and list length in flight while the
+    // current one is scored
+    constexpr unsigned FLAT_CHUNK = 8;
+    const unsigned n_pulls = nH + (nA + FLAT_CHUNK - 1) / FLAT_CHUNK;
     for (;;) {
         unsigned j = 0;
         if (lane == 0) j = atomicAdd(GG_FCTR(fv, s, 3), 1u);
         j = __shfl_sync(FULL, j, 0);
-        if (j >= nH + nA) break;
-        const bool hub_item = j < nH;                       // the hub items first: they are the long ones
-        const unsigned i = hub_item ? (unsigned)fv.hub[j] : j - nH;
-        int rec = 0;
-        if (!hub_item) {
-            rec = fv.item_n[i];
-            if ((rec & 0x3fffffff) < 2) continue;           // finished by flat_enum_kernel, or a hub item
-        }
-        const long long w = A[i];
-        const int cur = fv.cur[w], prev = fv.prev[w];
-        const int slot = __ldg(d.walk_slot + w);
-        const int root = d.roots[slot];
-        const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
-        int n, idx, nxt;
-        bool inc_father;
-        uint32_t a, b;
-        if (hub_item) {
-            inc_father = step_includes_father(d, s, s == 1 ? d.first_edge[w] : 0);
-            const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
-            int *ids; float *sc; float m;
-            build_list<CPL, UNR>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
-            if (n == 0) {
-                if (lane == 0) flat_void(d, s, w);
-                continue;
+        if (j >= n_pulls) break;
+        const bool hub_item = j < nH;
+        unsigned i = hub_item ? (unsigned)fv.hub[j] : (j - nH) * FLAT_CHUNK;
+        const unsigned i_end = hub_item ? i + 1 : ((i + FLAT_CHUNK < nA) ? i + FLAT_CHUNK : nA);
+        int4 rec_next = A[i];
+        int n_next = hub_item ? 0 : fv.item_n[i];
+        for (; i < i_end; ++i) {
+            const int4 rec = rec_next;
+            const int nrec = n_next;
+            if (i + 1 < i_end) { rec_next = A[i + 1]; n_next = fv.item_n[i + 1]; }
+            if (!hub_item && (nrec & 0x3fffffff) < 2) continue;      // finished by flat_enum_kernel, or a hub item
+            const long long w = rec.x;
+            const int cur = rec.y, prev = rec.z, slot = rec.w;
+            int n, idx, nxt;
+            bool inc_father;
+            uint32_t a, b;
+            if (hub_item) {
+                inc_father = step_includes_father(d, s, s == 1 ? d.first_edge[w] : 0);
+                const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
+                int *ids; float *sc; float m;
+                build_list<CPL, UNR>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
+                if (n == 0) {
+                    if (lane == 0) flat_void(d, s, w);
+                    continue;
+                }
+                philox4x32_10((uint32_t)d.roots[slot], (uint32_t)(w - __ldg(d.walk_ptr + slot)), (uint32_t)s, d.pass_tag, k0, k1, a, b);
+                idx = (n == 1) ? 0 : choose_index(sc, n, m, u53(a, b), lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
+                nxt = ids[idx];
+                __syncwarp();
+            } else {
+                n = nrec & 0x3fffffff;
+                inc_father = (nrec >> 30) & 1;
+                const int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
+                float4 c4[CPL];
+                load_row<CPL>(d.emb, d.ld, cur, lane & 7, c4);
+                const int root = d.roots[slot];
+                const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
+                score_list<CPL>(d.emb, d.bias, d.ld, c4, ids, s_sc, n, cur, lane);
+                rows_gathered += 1u + (unsigned)n;
+                const float m = list_max(s_sc, n, lane);
+                philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
+                idx = choose_index(s_sc, n, m, u53(a, b), lane);
+                nxt = ids[idx];
+                __syncwarp();
             }
-            philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
-            idx = (n == 1) ? 0 : choose_index(sc, n, m, u53(a, b), lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
-            nxt = ids[idx];
-            __syncwarp();
-        } else {
-            n = rec & 0x3fffffff;
-            inc_father = (rec >> 30) & 1;
-            const int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
-            float4 c4[CPL];
-            load_row<CPL>(d.emb, d.ld, cur, lane & 7, c4);
-            score_list<CPL>(d.emb, d.bias, d.ld, c4, ids, s_sc, n, cur, lane);
-            rows_gathered += 1u + (unsigned)n;
-            const float m = list_max(s_sc, n, lane);
-            philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
-            idx = choose_index(s_sc, n, m, u53(a, b), lane);
-            nxt = ids[idx];
-            __syncwarp();
+            if (lane == 0) flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
+            raw_steps += 1; raw_suml += (unsigned)n;
         }
-        if (lane == 0) flat_advance(d, fv, s, w, cur, n, idx, nxt, inc_father, overflow);
-        raw_steps += 1; raw_suml += (unsigned)n;
     }
     if (lane == 0) {
         if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
@@ -750,11 +762,11 @@ size_t flat_layout(void *buf, long long n_walks, int hub_threshold, int steps, F
         return p;
     };
     unsigned *ctr = (unsigned *)take(sizeof(unsigned) * FLAT_CTR_WORDS);
-    int *cur = (int *)take(4 * W), *prev = (int *)take(4 * W), *l0 = (int *)take(4 * W), *l1 = (int *)take(4 * W);
-    int *tail = (int *)take(4 * W), *hub = (int *)take(4 * W), *item_n = (int *)take(4 * W);
+    int4 *l0 = (int4 *)take(16 * W), *l1 = (int4 *)take(16 * W), *tail = (int4 *)take(16 * W);
+    int *hub = (int *)take(4 * W), *item_n = (int *)take(4 * W);
     int *pool = (int *)take(4 * W * (size_t)stride);
     if (fv) {
-        fv->ctr = ctr; fv->cur = cur; fv->prev = prev; fv->list[0] = l0; fv->list[1] = l1; fv->tail = tail; fv->hub = hub;
+        fv->ctr = ctr; fv->list[0] = l0; fv->list[1] = l1; fv->tail = tail; fv->hub = hub;
         fv->item_n = item_n; fv->pool_ids = pool; fv->stride = stride; fv->steps = steps;
     }
     return off;

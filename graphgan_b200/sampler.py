@@ -198,7 +198,7 @@ class WalkSampler:
         self.bfs_bottom_up_ratio = float(os.environ.get("GG_BFS_BU_RATIO", "-1"))
         self.bfs_flags = 0
         # level-synchronous walk steps (csrc/walk.cu: flat_*_kernel) for steps 1..flat_steps; 0 = persistent kernel only
-        self.flat_steps = int(os.environ.get("GG_FLAT_STEPS", "0"))
+        self.flat_steps = int(os.environ.get("GG_FLAT_STEPS", "4"))
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream

@@ -17,7 +17,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-FAMILIES = ["hub_score_kernel", "root_cdf_kernel", "root_step_kernel", "step1_cdf_kernel", "walk_kernel", "finalize_kernel",
+FAMILIES = ["hub_score_kernel", "root_cdf_kernel", "root_step_kernel", "step1_cdf_kernel", "flat_start_kernel", "flat_enum_kernel",
+            "flat_choose_kernel", "walk_kernel", "finalize_kernel",
             "emit_rows_kernel", "bfs_kernel", "adam_kernel", "reward_kernel", "pair_grad_kernel"]
 
 
@@ -54,10 +55,19 @@ def main():
     h = sys.argv[4] if len(sys.argv) > 4 else _build.source_hash()
     if doc.get("source_hash") != h:
         doc = {"source_hash": h, "kernels": {}, "detail": {}}
-    k1 = ["hub_score_kernel", "root_cdf_kernel", "root_step_kernel", "step1_cdf_kernel", "walk_kernel"]
+    walk = ["flat_start_kernel", "flat_enum_kernel", "flat_choose_kernel", "walk_kernel"]   # the walk stage (one walk_kernel per pass)
+    k1 = ["hub_score_kernel", "root_cdf_kernel", "root_step_kernel", "step1_cdf_kernel"] + walk
     entry = {f: per[f]["dram_bytes"] / per[f]["launches"] for f in per}
-    if all(f in per for f in ("hub_score_kernel", "root_cdf_kernel", "walk_kernel")):
-        entry["k1_stage"] = sum(entry[f] for f in k1 if f in entry)
+    if "walk_kernel" in per:
+        passes = per["walk_kernel"]["launches"]             # the capture must cover whole passes
+        entry["walk_stage"] = sum(per[f]["dram_bytes"] for f in walk if f in per) / passes
+        entry["walk_stage_ncu_us"] = sum(per[f]["time_ns"] for f in walk if f in per) / passes / 1e3
+        for f in ("flat_enum_kernel", "flat_choose_kernel", "flat_start_kernel"):
+            if f in per:
+                entry[f + "_per_pass"] = per[f]["dram_bytes"] / passes
+                entry[f + "_ncu_us_per_pass"] = per[f]["time_ns"] / passes / 1e3
+        if all(f in per for f in ("hub_score_kernel", "root_cdf_kernel")):
+            entry["k1_stage"] = sum(per[f]["dram_bytes"] for f in k1 if f in per) / passes
     doc["kernels"].setdefault(key, {}).update(entry)
     doc["detail"].setdefault(key, {}).update({f: {"launches": per[f]["launches"], "dram_bytes_per_launch": entry[f],
                                                    "ncu_time_us_per_launch": per[f]["time_ns"] / per[f]["launches"] / 1e3,
