@@ -627,7 +627,7 @@ def run_b200(args):
                     "call": "WalkSampler.precompute + run + finalize + emit_d_rows with pinned host roots in / rows out",
                     "note": "trees and the walk plan of these roots are resident (SURVEY 8d); a NEW root batch also costs "
                             "gg_bfs_build + the plan -- see full_pass"},
-            "gpu_launches": (((9 if smp.depth1 else 7) if reuse else 5) + ((1 + 2 * flat) if flat else 0)) * args.steps,
+            "gpu_launches": (((11 if smp.depth1 else 9) if reuse else 7) + ((1 + 2 * flat) if flat else 0)) * args.steps,
             "parity": parity,
             "roofline": {"bound": "hbm", "kernel": kname, "flat_steps": flat,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -110,6 +110,46 @@ __device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const 
         }
         return;
     }
+#if GG_ENUM_TWO_PHASE
+    if (cached) {
+        // ---- cached list that fits the shared score buffer, two phases: (1) the children's ENTRY NUMBERS from the bitmap
+        // words alone (ballots and popcounts, no dependent global load), (2) adjacency id and cached score of every
+        // child, four independent loads per lane in flight -- instead of one round trip per pair of bitmap words
+        const int n0 = n;
+        for (long long wb = wfirst; wb <= wlast; wb += 32) {
+            const long long wi = wb + lane;
+            unsigned word = (wi <= wlast) ? __ldg(tb + wi) : 0u;
+            if (wi == wfirst) word &= 0xffffffffu << (a0 & 31);
+            if (wi == wlast && (a1 & 31)) word &= (1u << (a1 & 31)) - 1u;
+            unsigned nz = __ballot_sync(FULL, word != 0u);
+            while (nz) {
+                const int j = __ffs(nz) - 1;
+                nz &= nz - 1u;
+                const unsigned wv = __shfl_sync(FULL, word, j);
+                if ((wv >> lane) & 1u) ids[n + __popc(wv & lt)] = (int)(((wb + j) << 5) + lane);
+                n += __popc(wv);
+            }
+        }
+        __syncwarp();
+        for (int i0 = n0; i0 < n; i0 += 128) {
+            int e[4], v[4];
+            float cs[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int i = i0 + 32 * k + lane; e[k] = (i < n) ? ids[i] : -1; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = (e[k] >= 0) ? __ldg(d.adj + e[k]) : -1;
+                cs[k] = (e[k] >= 0) ? __ldg(d.edge_score + e[k]) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + 32 * k + lane;
+                if (i < n) { ids[i] = v[k]; sc[i] = cs[k]; m = fmaxf(m, cs[k]); }
+            }
+        }
+        return;
+    }
+#endif
     for (long long wb = wfirst; wb <= wlast; wb += 32) {
         const long long wi = wb + lane;
         unsigned word = (wi <= wlast) ? __ldg(tb + wi) : 0u;
@@ -194,7 +234,28 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t
 
 // One complete walk, executed by a full warp.  Returns the status.
 // a (root, depth-1 child) pair gets a shared CDF (step1_cdf_kernel) when at least this many walks picked it
-constexpr int S1_MIN_WALKS = 2;
+#ifndef GG_S1_MIN_WALKS
+#define GG_S1_MIN_WALKS 1
+#endif
+#ifndef GG_S1_HUB_SINGLES
+#define GG_S1_HUB_SINGLES 0
+#endif
+constexpr int S1_MIN_WALKS = GG_S1_MIN_WALKS;
+
+// Does the pair (root slot, i-th neighbour) at `s1pos` get a shared CDF from step1_cdf_kernel?  GG_S1_HUB_SINGLES = 0: when
+// at least S1_MIN_WALKS walks picked it.  1: when two walks picked it, or one walk did and the child is score-cached (a
+// hub list is long: the queue of step1_cdf_kernel starts the longest first; a short list picked once is cheaper as an
+// item of the first level-synchronous step).  deg(child) + 1 = s1_ptr[pos + 1] - s1_ptr[pos].
+__device__ __forceinline__ bool s1_is_shared(const gg_walk_desc &d, long long s1pos) {
+    const int cnt = __ldg(d.s1_cnt + s1pos);
+#if GG_S1_HUB_SINGLES
+    if (cnt >= 2) return true;
+    if (cnt < 1) return false;
+    return d.edge_score && (__ldg(d.s1_ptr + s1pos + 1) - __ldg(d.s1_ptr + s1pos) - 1) >= d.hub_threshold;
+#else
+    return cnt >= S1_MIN_WALKS;
+#endif
+}
 
 // where a walk (re)starts: a fresh walk stands on its root; a walk handed over by the level-synchronous steps
 // (flat_*_kernel below) continues from the node it reached (step == choices made so far)
@@ -231,7 +292,7 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
         long long s1pos = -1;     // slice of the depth-1 cache, when this (root, child) pair was picked by >= 2 walks
         if (step == 1 && d.s1_q) {
             s1pos = __ldg(d.rq_ptr + slot) + (fedge - d.indptr[root]);
-            if (__ldg(d.s1_cnt + s1pos) < S1_MIN_WALKS) s1pos = -1;
+            if (!s1_is_shared(d, s1pos)) s1pos = -1;
         }
         if (step == 0 && d.root_q) {
             // ---- root step from the per-root CDF (hub.cu: root_cdf_kernel): every walk of a root
@@ -370,7 +431,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) step1_cdf_k
             pos = item;
             item += nwarps;
         }
-        if (__ldg(d.s1_cnt + pos) < S1_MIN_WALKS) continue;   // a pair picked once is cheaper inside its walk (no CDF array)
+        if (!s1_is_shared(d, pos)) continue;
         const int slot = __ldg(d.s1_slot + pos);
         const int root = d.roots[slot];
         const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
@@ -562,7 +623,7 @@ __global__ void __launch_bounds__(256) flat_start_kernel(const __grid_constant__
                 if (prow && 1 < d.max_path) prow[1] = c;
                 ws = 1; wl = n0; steps = 1; suml = (unsigned)n0;
                 const long long s1pos = __ldg(d.rq_ptr + slot) + fi;
-                if (__ldg(d.s1_cnt + s1pos) >= S1_MIN_WALKS) {
+                if (s1_is_shared(d, s1pos)) {
                     const int n = __ldg(d.s1_n + s1pos);
                     if (n == 0) {
                         status = GG_VOID;                   // graph_gan.py:255-257
@@ -714,7 +775,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
                 inc_father = step_includes_father(d, s, s == 1 ? d.first_edge[w] : 0);
                 const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
                 int *ids; float *sc; float m;
-                build_list<CPL, UNR>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
+                build_list<CPL, GG_UNR_HUB>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
                 if (n == 0) {
                     if (lane == 0) flat_void(d, s, w);
                     continue;
@@ -818,52 +879,51 @@ __global__ void __launch_bounds__(32) walk_stream_kernel(const __grid_constant__
     }
 }
 
-// ---------------------------------------------------------------- finalize (one warp per root)
-__global__ void finalize_kernel(long long n_roots, const long long *walk_ptr, int for_d, int *samples, int *status,
-                                const int *first_edge, int *wsteps, int *wsuml, int *path_len, uint32_t *d1_bits,
-                                int *root_ok, unsigned long long *counters) {
-    const int lane = threadIdx.x & 31;
-    const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (slot >= n_roots) return;
-    const long long w0 = walk_ptr[slot], w1 = walk_ptr[slot + 1];
-    // first walk that is not DONE (void, skipped or never run); four independent loads in flight per lane (a hub
-    // root has > 10 k walks and one warp)
-    long long first_bad = w1;
-    for (long long w = w0 + lane; w < w1 && first_bad == w1; w += 128) {
-        int st[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) st[q] = (w + 32 * q < w1) ? status[w + 32 * q] : GG_DONE;
-#pragma unroll
-        for (int q = 3; q >= 0; --q) if (st[q] != GG_DONE) first_bad = w + 32 * q;
+// ---------------------------------------------------------------- finalize (thread per walk)
+// Three flat passes instead of one warp per root (a hub root has > 10 k walks: its warp was the launch's tail):
+//   1. every walk that is not DONE lowers its root's "first bad walk" (atomicMin into root_ok, used as scratch)
+//   2. every walk up to and including the first bad one adds its counters and (D mode) its father-removal bit;
+//      the walks after it are blanked -- the reference never ran them (graph_gan.py:252-257 returned early)
+//   3. per root: root_ok = no bad walk and at least one walk ("neg is not None and len(pos) != 0", graph_gan.py:192)
+constexpr int FIN_NONE = 0x7f7f7f7f;                      // (the memset pattern root_ok is initialised with)
+
+__device__ __forceinline__ long long walk_root_slot(const long long *__restrict__ walk_ptr, long long n_roots, long long w) {
+    long long lo = 0, hi = n_roots;                         // last slot with walk_ptr[slot] <= w
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(walk_ptr + mid) <= w) lo = mid; else hi = mid;
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const long long o = __shfl_xor_sync(FULL, first_bad, off);
-        first_bad = o < first_bad ? o : first_bad;
+    return lo;
+}
+
+__global__ void finalize_mark_kernel(long long n_roots, const long long *__restrict__ walk_ptr, const int *__restrict__ status,
+                                     int *root_ok) {
+    const long long W = walk_ptr[n_roots];
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (long long)gridDim.x * blockDim.x) {
+        if (status[w] == GG_DONE) continue;
+        const long long slot = walk_root_slot(walk_ptr, n_roots, w);
+        atomicMin(root_ok + slot, (int)(w - walk_ptr[slot]));
     }
-    const bool ok = (first_bad == w1) && (w1 > w0);
+}
+
+__global__ void finalize_apply_kernel(long long n_roots, const long long *__restrict__ walk_ptr, int for_d, int *samples,
+                                      int *status, const int *__restrict__ first_edge, int *wsteps, int *wsuml, int *path_len,
+                                      uint32_t *d1_bits, const int *__restrict__ root_ok, unsigned long long *counters) {
+    const long long W = walk_ptr[n_roots];
     unsigned long long steps = 0, suml = 0;
-    for (long long wb = w0 + lane; wb < w1; wb += 128) {
-        int st[4], ws[4], wl[4], fe[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const long long w = wb + 32 * q;
-            const bool in = w < w1 && w <= first_bad;
-            st[q] = in ? status[w] : GG_NOTRUN; ws[q] = in ? wsteps[w] : 0; wl[q] = in ? wsuml[w] : 0;
-            fe[q] = (in && for_d) ? first_edge[w] : -1;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const long long w = wb + 32 * q;
-            if (w >= w1) break;
-            if (w <= first_bad) {
-                steps += (unsigned)ws[q]; suml += (unsigned)wl[q];
-                if (for_d && st[q] == GG_DONE && fe[q] >= 0) atomicOr(d1_bits + (fe[q] >> 5), 1u << (fe[q] & 31));
-            } else {  // the reference never ran these (graph_gan.py:252-257 returned early)
-                if (status[w] != GG_SKIPPED) status[w] = GG_NOTRUN;
-                samples[w] = -1; wsteps[w] = 0; wsuml[w] = 0;
-                if (path_len) path_len[w] = 0;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (long long)gridDim.x * blockDim.x) {
+        const long long slot = walk_root_slot(walk_ptr, n_roots, w);
+        const long long off = w - walk_ptr[slot];
+        if (off <= (long long)root_ok[slot]) {
+            steps += (unsigned)wsteps[w]; suml += (unsigned)wsuml[w];
+            if (for_d && status[w] == GG_DONE) {
+                const int fe = first_edge[w];
+                if (fe >= 0) atomicOr(d1_bits + (fe >> 5), 1u << (fe & 31));
             }
+        } else {
+            if (status[w] != GG_SKIPPED) status[w] = GG_NOTRUN;
+            samples[w] = -1; wsteps[w] = 0; wsuml[w] = 0;
+            if (path_len) path_len[w] = 0;
         }
     }
 #pragma unroll
@@ -871,14 +931,30 @@ __global__ void finalize_kernel(long long n_roots, const long long *walk_ptr, in
         steps += __shfl_xor_sync(FULL, steps, off);
         suml += __shfl_xor_sync(FULL, suml, off);
     }
-    if (lane == 0) {
-        root_ok[slot] = ok ? 1 : 0;
+    if ((threadIdx.x & 31) == 0) {
         if (steps) atomicAdd(counters + GG_CNT_STEPS, steps);
         if (suml) atomicAdd(counters + GG_CNT_SUML, suml);
-        if (ok) {
-            atomicAdd(counters + GG_CNT_ACCEPTED, (unsigned long long)(w1 - w0));
-            atomicAdd(counters + GG_CNT_OK_ROOTS, 1ull);
-        }
+    }
+}
+
+__global__ void finalize_roots_kernel(long long n_roots, const long long *__restrict__ walk_ptr, int *root_ok,
+                                      unsigned long long *counters) {
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long acc = 0, okr = 0;
+    if (slot < n_roots) {
+        const long long k = walk_ptr[slot + 1] - walk_ptr[slot];
+        const bool ok = root_ok[slot] == FIN_NONE && k > 0;
+        root_ok[slot] = ok ? 1 : 0;
+        if (ok) { acc = (unsigned long long)k; okr = 1; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        acc += __shfl_xor_sync(FULL, acc, off);
+        okr += __shfl_xor_sync(FULL, okr, off);
+    }
+    if ((threadIdx.x & 31) == 0 && okr) {
+        atomicAdd(counters + GG_CNT_ACCEPTED, acc);
+        atomicAdd(counters + GG_CNT_OK_ROOTS, okr);
     }
 }
 
@@ -888,18 +964,19 @@ __global__ void row_count_kernel(long long n_roots, const long long *walk_ptr, c
     if (i < n_roots) row_ptr[i] = root_ok[i] ? 2 * (walk_ptr[i + 1] - walk_ptr[i]) : 0;
 }
 
-__global__ void emit_rows_kernel(long long n_roots, const int *roots, const long long *walk_ptr,
-                                 const long long *pos_indptr, const int *pos_flat, const int *root_ok,
-                                 const int *samples, const long long *row_ptr, int *center, int *neighbor, int *label) {
-    const int lane = threadIdx.x & 31;
-    const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (slot >= n_roots || !root_ok[slot]) return;
-    const int r = roots[slot];
-    const long long k = walk_ptr[slot + 1] - walk_ptr[slot];
-    const long long o = row_ptr[slot], p0 = pos_indptr[r], w0 = walk_ptr[slot];
-    for (long long t = lane; t < k; t += 32) {  // graph_gan.py:194-201
-        center[o + t] = r; neighbor[o + t] = pos_flat[p0 + t]; label[o + t] = 1;
-        center[o + k + t] = r; neighbor[o + k + t] = samples[w0 + t]; label[o + k + t] = 0;
+// thread per walk: its positive row and its negative row (graph_gan.py:194-201)
+__global__ void emit_rows_kernel(long long n_roots, const int *__restrict__ roots, const long long *__restrict__ walk_ptr,
+                                 const long long *__restrict__ pos_indptr, const int *__restrict__ pos_flat,
+                                 const int *__restrict__ root_ok, const int *__restrict__ samples,
+                                 const long long *__restrict__ row_ptr, int *center, int *neighbor, int *label) {
+    const long long W = walk_ptr[n_roots];
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (long long)gridDim.x * blockDim.x) {
+        const long long slot = walk_root_slot(walk_ptr, n_roots, w);
+        if (!root_ok[slot]) continue;
+        const int r = roots[slot];
+        const long long w0 = walk_ptr[slot], k = walk_ptr[slot + 1] - w0, t = w - w0, o = row_ptr[slot];
+        center[o + t] = r; neighbor[o + t] = pos_flat[pos_indptr[r] + t]; label[o + t] = 1;
+        center[o + k + t] = r; neighbor[o + k + t] = samples[w]; label[o + k + t] = 0;
     }
 }
 
@@ -1048,11 +1125,17 @@ extern "C" int gg_walk_finalize(int64_t n_roots, const int64_t *walk_ptr, int32_
     GG_REQUIRE(walk_ptr && samples && status && first_edge && wsteps && wsuml && root_ok && counters, "null pointer");
     GG_REQUIRE(!for_d || d1_bits, "D mode needs d1_bits");
     if (n_roots == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
     const int threads = 256;
-    const long long blocks = (n_roots * 32 + threads - 1) / threads;
-    gg::finalize_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        n_roots, (const long long *)walk_ptr, for_d, samples, status, first_edge, wsteps, wsuml, path_len, d1_bits,
-        root_ok, counters);
+    const unsigned wgrid = (unsigned)(gg::sm_count() * 8);           // grid-stride over the walks (their number is on the device)
+    GG_CHECK(cudaMemsetAsync(root_ok, 0x7f, sizeof(int32_t) * (size_t)n_roots, st));
+    gg::finalize_mark_kernel<<<wgrid, threads, 0, st>>>(n_roots, (const long long *)walk_ptr, status, root_ok);
+    GG_CHECK(cudaGetLastError());
+    gg::finalize_apply_kernel<<<wgrid, threads, 0, st>>>(n_roots, (const long long *)walk_ptr, for_d, samples, status, first_edge,
+                                                        wsteps, wsuml, path_len, d1_bits, root_ok, counters);
+    GG_CHECK(cudaGetLastError());
+    gg::finalize_roots_kernel<<<(unsigned)((n_roots + threads - 1) / threads), threads, 0, st>>>(
+        n_roots, (const long long *)walk_ptr, root_ok, counters);
     return gg::check_cuda(cudaGetLastError(), "finalize kernel launch");
 }
 
@@ -1073,8 +1156,7 @@ extern "C" int gg_emit_d_rows(int64_t n_roots, const int32_t *roots, const int64
     if (rc) return rc;
     if (n_roots == 0) return 0;
     GG_REQUIRE(center && neighbor && label, "null output pointer");
-    const long long blocks = (n_roots * 32 + threads - 1) / threads;
-    gg::emit_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(n_roots, roots, (const long long *)walk_ptr,
+    gg::emit_rows_kernel<<<(unsigned)(gg::sm_count() * 8), threads, 0, st>>>(n_roots, roots, (const long long *)walk_ptr,
                                                                (const long long *)pos_indptr, pos_flat, root_ok,
                                                                samples, (const long long *)row_ptr, center, neighbor,
                                                                label);

@@ -18,6 +18,12 @@ namespace gg {
 #ifndef GG_UNR_S1
 #define GG_UNR_S1 8
 #endif
+#ifndef GG_UNR_HUB
+#define GG_UNR_HUB GG_UNR     // bitmap words in flight when flat_choose_kernel enumerates a cached (hub) list
+#endif
+#ifndef GG_ENUM_TWO_PHASE
+#define GG_ENUM_TWO_PHASE 0   // cached lists below the TMA-staging size: entry numbers first, then ids + scores (A/B)
+#endif
 #ifndef GG_WALK_MIN_CTAS
 #define GG_WALK_MIN_CTAS 4
 #endif
@@ -56,10 +62,15 @@ __device__ __forceinline__ void score_list(const float *__restrict__ emb, const 
                                            const float4 (&c4)[CPL], const int *ids, float *sc, int n, int fallback,
                                            int lane) {
     const int grp = lane >> 3, g = lane & 7;
+    // (the ids of the NEXT eight candidates are fetched while this iteration's rows are in flight: the id -> row
+    // dependency costs one exposed round trip per list instead of one per iteration)
+    int ca_n = (grp < n) ? ids[grp] : fallback, cb_n = (4 + grp < n) ? ids[4 + grp] : fallback;
     for (int i0 = 0; i0 < n; i0 += 8) {
         const int ia = i0 + grp, ib = i0 + 4 + grp;
         const bool va = ia < n, vb = ib < n;
-        const int ca = va ? ids[ia] : fallback, cb = vb ? ids[ib] : fallback;
+        const int ca = ca_n, cb = cb_n;
+        ca_n = (ia + 8 < n) ? ids[ia + 8] : fallback;
+        cb_n = (ib + 8 < n) ? ids[ib + 8] : fallback;
         const float *ra = emb + (size_t)ca * (size_t)ld + 4 * g;
         const float *rb = emb + (size_t)cb * (size_t)ld + 4 * g;
         float4 xa[CPL], xb[CPL];
@@ -89,10 +100,13 @@ __device__ __forceinline__ void score_edges(const float *__restrict__ emb, const
                                             const float4 (&c4)[CPL], const int *__restrict__ adj, long long e0,
                                             int n, float *out, int fallback, int lane) {
     const int grp = lane >> 3, g = lane & 7;
+    int ca_n = (grp < n) ? __ldg(adj + e0 + grp) : fallback, cb_n = (4 + grp < n) ? __ldg(adj + e0 + 4 + grp) : fallback;
     for (int i0 = 0; i0 < n; i0 += 8) {
         const int ia = i0 + grp, ib = i0 + 4 + grp;
         const bool va = ia < n, vb = ib < n;
-        const int ca = va ? __ldg(adj + e0 + ia) : fallback, cb = vb ? __ldg(adj + e0 + ib) : fallback;
+        const int ca = ca_n, cb = cb_n;          // (next iteration's ids in flight behind this iteration's rows, see score_list)
+        ca_n = (ia + 8 < n) ? __ldg(adj + e0 + ia + 8) : fallback;
+        cb_n = (ib + 8 < n) ? __ldg(adj + e0 + ib + 8) : fallback;
         const float *ra = emb + (size_t)ca * (size_t)ld + 4 * g;
         const float *rb = emb + (size_t)cb * (size_t)ld + 4 * g;
         float4 xa[CPL], xb[CPL];
