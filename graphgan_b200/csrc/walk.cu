@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
     const int4 *A = fv.list[s & 1];
     const unsigned nA = *GG_FCTR(fv, s, 0), nH = *GG_FCTR(fv, s, 1);
     const uint32_t k0 = (uint32_t)d.seed, k1 = (uint32_t)(d.seed >> 32);
-    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0, rows_small = 0;
     unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
     // work queue: the hub items first, one per pull (they are the long ones); then the other items in chunks of
     // FLAT_CHUNK consecutive list positions per pull, the next item's record and list length in flight while the
@@ -759,13 +759,84 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
         const bool hub_item = j < nH;
         unsigned i = hub_item ? (unsigned)fv.hub[j] : (j - nH) * FLAT_CHUNK;
         const unsigned i_end = hub_item ? i + 1 : ((i + FLAT_CHUNK < nA) ? i + FLAT_CHUNK : nA);
+#if GG_FLAT_SUBWARP
+        if (!hub_item) {
+            // ---- short lists (2..8 candidates: most items beyond step 1), FOUR items at a time, one per 8-lane group.
+            // The canonical sequence on <= 8 candidates only ever combines lanes 0..7 of the 32-lane form with exact zeros
+            // (butterfly sum: x + 0 == x at the xor-16 / xor-8 stages; Kogge-Stone scan: lanes 0..7 take nothing from
+            // offsets 8 and 16, and lane 31 ends as 0 + ... + scan_7), so an 8-lane group reproduces it bit for bit.
+            const int grp = lane >> 3, l8 = lane & 7, gbase = lane & 24;
+            for (unsigned ib = i; ib < i_end; ib += 4) {
+                const unsigned it = ib + (unsigned)grp;
+                const bool have = it < i_end;
+                const int4 rec = have ? A[it] : make_int4(0, 0, 0, 0);
+                const int nrec = have ? fv.item_n[it] : 0;
+                const int n = nrec & 0x3fffffff;
+                const bool small = have && n >= 2 && n <= 8;
+                if (!__any_sync(FULL, small)) continue;
+                const long long w = rec.x;
+                const int cur = small ? rec.y : 0, slot = rec.w;
+                const bool inc_father = (nrec >> 30) & 1;
+                const int *ids = fv.pool_ids + (size_t)it * (size_t)fv.stride;
+                const int my_id = (small && l8 < n) ? ids[l8] : cur;
+                float4 c4[CPL];
+                load_row<CPL>(d.emb, d.ld, cur, l8, c4);
+                const int root = small ? d.roots[slot] : 0;
+                const uint32_t k = small ? (uint32_t)(w - __ldg(d.walk_ptr + slot)) : 0u;
+                const int nmax = __reduce_max_sync(FULL, small ? n : 0);
+                float score = 0.0f;
+                for (int j = 0; j < nmax; j += 2) {
+                    const int ca = __shfl_sync(FULL, my_id, gbase + j), cb = __shfl_sync(FULL, my_id, gbase + j + 1);
+                    const float *ra = d.emb + (size_t)ca * (size_t)d.ld + 4 * l8;
+                    const float *rb = d.emb + (size_t)cb * (size_t)d.ld + 4 * l8;
+                    float4 xa[CPL], xb[CPL];
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) xa[c] = ldg4(ra + 32 * c);
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) xb[c] = ldg4(rb + 32 * c);
+                    const float ba = __ldg(d.bias + ca), bb = __ldg(d.bias + cb);
+                    float sa = 0.0f, sb = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) sa = fma4(c4[c], xa[c], sa);
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) sb = fma4(c4[c], xb[c], sb);
+                    sa = group8_sum(sa);
+                    sb = group8_sum(sb);
+                    if (l8 == j) score = __fadd_rn(sa, ba);
+                    if (l8 == j + 1) score = __fadd_rn(sb, bb);
+                }
+                const bool mine = small && l8 < n;
+                float m = mine ? score : -INFINITY;
+                m = fmaxf(m, __shfl_xor_sync(FULL, m, 4)); m = fmaxf(m, __shfl_xor_sync(FULL, m, 2)); m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
+                const float e = mine ? exp_c(__fsub_rn(score, m)) : 0.0f;
+                const float S = group8_sum(e);                         // == warp_sum_butterfly over (e_0..e_7, 0, ..., 0)
+                double x = (double)__fdiv_rn(e, small ? S : 1.0f);
+#pragma unroll
+                for (int off = 1; off < 8; off <<= 1) {
+                    const double y = __shfl_up_sync(FULL, x, off, 8);
+                    if (l8 >= off) x = __dadd_rn(x, y);
+                }
+                const double total = __shfl_sync(FULL, x, gbase + 7);   // == lane 31 of the 32-lane scan
+                uint32_t a, b;
+                philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
+                const double u = u53(a, b);
+                const unsigned hit = (__ballot_sync(FULL, mine && (__ddiv_rn(x, small ? total : 1.0) > u)) >> gbase) & 0xffu;
+                const int idx = hit ? __ffs(hit) - 1 : n - 1;
+                const int nxt = __shfl_sync(FULL, my_id, gbase + (small ? idx : 0));
+                if (small && l8 == 0) {
+                    flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
+                    raw_steps += 1; raw_suml += (unsigned)n; rows_small += 1u + (unsigned)n;
+                }
+            }
+        }
+#endif
         int4 rec_next = A[i];
         int n_next = hub_item ? 0 : fv.item_n[i];
         for (; i < i_end; ++i) {
             const int4 rec = rec_next;
             const int nrec = n_next;
             if (i + 1 < i_end) { rec_next = A[i + 1]; n_next = fv.item_n[i + 1]; }
-            if (!hub_item && (nrec & 0x3fffffff) < 2) continue;      // finished by flat_enum_kernel, or a hub item
+            if (!hub_item && (nrec & 0x3fffffff) < (GG_FLAT_SUBWARP ? 9 : 2)) continue;   // finished by flat_enum_kernel / a hub item / done above
             const long long w = rec.x;
             const int cur = rec.y, prev = rec.z, slot = rec.w;
             int n, idx, nxt;
@@ -800,10 +871,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
                 nxt = ids[idx];
                 __syncwarp();
             }
-            if (lane == 0) flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
-            raw_steps += 1; raw_suml += (unsigned)n;
+            if (lane == 0) {
+                flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
+                raw_steps += 1; raw_suml += (unsigned)n;
+            }
         }
     }
+    // lane 0 counted the full-warp items, lane 0 of every 8-lane group (lanes 0, 8, 16, 24) its short ones; rows_gathered
+    // (hub and long-list path) is warp-uniform, rows_small per group
+#pragma unroll
+    for (int off = 16; off >= 8; off >>= 1) {
+        raw_steps += __shfl_xor_sync(FULL, raw_steps, off); raw_suml += __shfl_xor_sync(FULL, raw_suml, off);
+        overflow += __shfl_xor_sync(FULL, overflow, off); rows_small += __shfl_xor_sync(FULL, rows_small, off);
+    }
+    rows_gathered += rows_small;
     if (lane == 0) {
         if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
         if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
