@@ -17,8 +17,8 @@
 //     8 consecutive entries per thread (one 32-B sector);
 //   * inside a chunk, several frontier nodes may reach the same undiscovered node: every candidate entry proposes
 //     key = (chunk-local index of its source, tag of the head) into a 16 k-slot shared table indexed by the head's low
-//     bits, keeping the minimum (plain load / compare / store iterated to a fixed point: shared-memory atomics are the
-//     slower way).  After a barrier the slot's minimum decides: same key -> this entry is THE tree edge;
+//     bits, keeping the minimum (one shared-memory atomicMin per candidate entry -- a few per cent of the entries -- and
+//     one barrier).  After the barrier the slot's minimum decides: same key -> this entry is THE tree edge;
 //     same head, other key -> an earlier father won; other head -> hash collision, the entry stays pending and the
 //     round repeats (rare: the table is at most half full).  Earlier chunks have already set their winners' visited
 //     bits, so "first in queue order" holds across chunks as well;
@@ -34,12 +34,6 @@
 namespace gg {
 namespace {
 
-#ifndef GG_BFS_ATOMIC_MIN
-#define GG_BFS_ATOMIC_MIN 1
-#endif
-#ifndef GG_BFS_DEFER
-#define GG_BFS_DEFER 0
-#endif
 constexpr int BFS_THREADS = 1024;
 constexpr int BFS_EPT = 8;                                 // adjacency entries per thread per slab
 constexpr unsigned BFS_SLAB = BFS_THREADS * BFS_EPT;       // 8192 entries
@@ -451,10 +445,6 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                 lo = hi; hi = tail;
                 continue;
             }
-#if GG_BFS_DEFER
-            unsigned dq_a = 0, dq_b = 0, dq_w = 0, dq_pos = 0;   // this thread's winner of the previous slab (see below)
-            bool dq_valid = false;
-#endif
             unsigned pf_i = 0xffffffffu;                    // prefetched window (valid inside a level only)
             uint2 pf = make_uint2(0u, 0u);
             for (unsigned wbase = lo; wbase < hi; wbase += BFS_THREADS) {
@@ -537,37 +527,14 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                                 for (int x = 0; x < BFS_EPT; ++x) key[x] |= ((unsigned)w[x] >> BFS_HBITS) & tagmask;
                             }
                             for (;;) {
-                                // slot minimum WITHOUT atomics (shared-memory atomics cost ~2 cycles per lane, plain LDS / STS
-                                // a fraction of that): every candidate whose key is below the slot's value stores it; stores
-                                // race, so repeat until nobody had to store -- then every slot holds its minimum (the owner of
-                                // a smaller key would still be storing).  One contender per slot drops out per iteration.
-#if GG_BFS_ATOMIC_MIN
-                                // (A/B) one shared-memory atomicMin per CANDIDATE entry (a few per cent of the entries) and one
-                                // barrier, instead of the barrier-per-round fixed point
+                                // slot minimum: one shared-memory atomicMin per CANDIDATE entry (a few per cent of the entries) and
+                                // one barrier (a barrier-per-round fixed point of plain stores was the top stall of the sweep)
                                 if (pend) {
 #pragma unroll
                                     for (int x = 0; x < BFS_EPT; ++x)
                                         if ((pend >> x) & 1u) atomicMin(table + ((unsigned)w[x] & (BFS_HSLOTS - 1)), key[x]);
                                 }
                                 __syncthreads();
-#else
-                                {
-                                    unsigned act = pend;
-                                    for (;;) {
-                                        unsigned wrote = 0;
-                                        if (act) {
-#pragma unroll
-                                            for (int x = 0; x < BFS_EPT; ++x) {
-                                                if (!((act >> x) & 1u)) continue;
-                                                volatile unsigned *slot = table + ((unsigned)w[x] & (BFS_HSLOTS - 1));
-                                                if (key[x] < *slot) { *slot = key[x]; wrote |= 1u << x; }
-                                                else act &= ~(1u << x);
-                                            }
-                                        }
-                                        if (!__syncthreads_or(wrote != 0u)) break;
-                                    }
-                                }
-#endif
                                 unsigned still = 0;
                                 if (pend) {
 #pragma unroll
@@ -612,26 +579,7 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                             }
                         }
                         __syncthreads();
-#if GG_BFS_DEFER
-                        // (A/B) the winner's adjacency range is a random 8-byte read that misses L2 more often than not: it is
-                        // issued here and CONSUMED one slab later (dq_*), behind the next slab's adjacency loads and table rounds
-                        if (dq_valid) {
-                            Q[dq_pos] = make_uint2(dq_a, dq_b - dq_a);
-                            pos[dq_w] = dq_pos;
-                            deg_acc += dq_b - dq_a;
-                            dq_valid = false;
-                        }
-                        if ((unsigned)tid < ntot) {
-                            const unsigned wv = table[2 * tid], e = table[2 * tid + 1];
-                            table[2 * tid] = BFS_EMPTY; table[2 * tid + 1] = BFS_EMPTY;
-                            dq_a = ip32[2 * (size_t)wv]; dq_b = ip32[2 * (size_t)wv + 2];
-                            dq_w = wv; dq_pos = tail + (unsigned)tid; dq_valid = true;
-                            atomicOr(tb + (e >> 5), 1u << (e & 31));
-                        }
-                        for (unsigned i = tid + BFS_THREADS; i < ntot; i += BFS_THREADS) {
-#else
                         for (unsigned i = tid; i < ntot; i += BFS_THREADS) {
-#endif
                             const unsigned wv = table[2 * i], e = table[2 * i + 1];
                             table[2 * i] = BFS_EMPTY; table[2 * i + 1] = BFS_EMPTY;
                             const unsigned qa = ip32[2 * (size_t)wv], qb = ip32[2 * (size_t)wv + 2];
@@ -641,25 +589,13 @@ bfs_kernel(long long n_node, const long long *__restrict__ indptr, const int *__
                             atomicOr(tb + (e >> 5), 1u << (e & 31));
                         }
                         tail += ntot;
-#if GG_BFS_ATOMIC_MIN
-                        // the table reads / resets above must be over before the next slab's atomicMin proposals (the fixed-point
-                        // loop re-stores a proposal that a late reset wiped; a single atomicMin cannot)
+                        // the table reads / resets above must be over before the next slab's atomicMin proposals (a late
+                        // reset would wipe a proposal)
                         if (!single || s0 + BFS_SLAB < Kend) __syncthreads();
-#else
-                        if (single && s0 + BFS_SLAB < Kend) __syncthreads();   // next slab of the same node: *s_win is not used
-#endif
                     }
                     jlo += m;
                 }
             }
-#if GG_BFS_DEFER
-            if (dq_valid) {
-                Q[dq_pos] = make_uint2(dq_a, dq_b - dq_a);
-                pos[dq_w] = dq_pos;
-                deg_acc += dq_b - dq_a;
-                dq_valid = false;
-            }
-#endif
             {                                               // adjacency entries of the next frontier
                 unsigned tot2;
                 block_scan_incl(deg_acc, s_tot + 32 * (flip ^= 1u), tot2);

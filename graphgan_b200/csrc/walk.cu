@@ -110,46 +110,6 @@ __device__ __forceinline__ void enumerate_children(const gg_walk_desc &d, const 
         }
         return;
     }
-#if GG_ENUM_TWO_PHASE
-    if (cached) {
-        // ---- cached list that fits the shared score buffer, two phases: (1) the children's ENTRY NUMBERS from the bitmap
-        // words alone (ballots and popcounts, no dependent global load), (2) adjacency id and cached score of every
-        // child, four independent loads per lane in flight -- instead of one round trip per pair of bitmap words
-        const int n0 = n;
-        for (long long wb = wfirst; wb <= wlast; wb += 32) {
-            const long long wi = wb + lane;
-            unsigned word = (wi <= wlast) ? __ldg(tb + wi) : 0u;
-            if (wi == wfirst) word &= 0xffffffffu << (a0 & 31);
-            if (wi == wlast && (a1 & 31)) word &= (1u << (a1 & 31)) - 1u;
-            unsigned nz = __ballot_sync(FULL, word != 0u);
-            while (nz) {
-                const int j = __ffs(nz) - 1;
-                nz &= nz - 1u;
-                const unsigned wv = __shfl_sync(FULL, word, j);
-                if ((wv >> lane) & 1u) ids[n + __popc(wv & lt)] = (int)(((wb + j) << 5) + lane);
-                n += __popc(wv);
-            }
-        }
-        __syncwarp();
-        for (int i0 = n0; i0 < n; i0 += 128) {
-            int e[4], v[4];
-            float cs[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { const int i = i0 + 32 * k + lane; e[k] = (i < n) ? ids[i] : -1; }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                v[k] = (e[k] >= 0) ? __ldg(d.adj + e[k]) : -1;
-                cs[k] = (e[k] >= 0) ? __ldg(d.edge_score + e[k]) : 0.0f;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = i0 + 32 * k + lane;
-                if (i < n) { ids[i] = v[k]; sc[i] = cs[k]; m = fmaxf(m, cs[k]); }
-            }
-        }
-        return;
-    }
-#endif
     for (long long wb = wfirst; wb <= wlast; wb += 32) {
         const long long wi = wb + lane;
         unsigned word = (wi <= wlast) ? __ldg(tb + wi) : 0u;
@@ -237,24 +197,13 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t
 #ifndef GG_S1_MIN_WALKS
 #define GG_S1_MIN_WALKS 1
 #endif
-#ifndef GG_S1_HUB_SINGLES
-#define GG_S1_HUB_SINGLES 0
-#endif
 constexpr int S1_MIN_WALKS = GG_S1_MIN_WALKS;
 
-// Does the pair (root slot, i-th neighbour) at `s1pos` get a shared CDF from step1_cdf_kernel?  GG_S1_HUB_SINGLES = 0: when
-// at least S1_MIN_WALKS walks picked it.  1: when two walks picked it, or one walk did and the child is score-cached (a
-// hub list is long: the queue of step1_cdf_kernel starts the longest first; a short list picked once is cheaper as an
-// item of the first level-synchronous step).  deg(child) + 1 = s1_ptr[pos + 1] - s1_ptr[pos].
+// Does the pair (root slot, i-th neighbour) at `s1pos` get a shared CDF from step1_cdf_kernel?  With S1_MIN_WALKS = 1: every
+// pair that was picked (measured: hub lists are long and the builder's queue starts the longest first; 2 -- pairs picked
+// once stay inside their walk -- and "2, or 1 when the child is score-cached" were both slower with the flat steps).
 __device__ __forceinline__ bool s1_is_shared(const gg_walk_desc &d, long long s1pos) {
-    const int cnt = __ldg(d.s1_cnt + s1pos);
-#if GG_S1_HUB_SINGLES
-    if (cnt >= 2) return true;
-    if (cnt < 1) return false;
-    return d.edge_score && (__ldg(d.s1_ptr + s1pos + 1) - __ldg(d.s1_ptr + s1pos) - 1) >= d.hub_threshold;
-#else
-    return cnt >= S1_MIN_WALKS;
-#endif
+    return __ldg(d.s1_cnt + s1pos) >= S1_MIN_WALKS;
 }
 
 // where a walk (re)starts: a fresh walk stands on its root; a walk handed over by the level-synchronous steps
@@ -719,7 +668,7 @@ __global__ void __launch_bounds__(FLAT_ENUM_WARPS * 32, 6) flat_enum_kernel(cons
     }
 }
 
-template <int CPL>
+template <int CPL, bool HUB_ONLY>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose_kernel(const __grid_constant__ gg_walk_desc d,
                                                                                         const FlatView fv, const int s) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
@@ -744,13 +693,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
     const int4 *A = fv.list[s & 1];
     const unsigned nA = *GG_FCTR(fv, s, 0), nH = *GG_FCTR(fv, s, 1);
     const uint32_t k0 = (uint32_t)d.seed, k1 = (uint32_t)(d.seed >> 32);
-    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0, rows_small = 0;
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
     unsigned int cyc[7] = {0, 0, 0, 0, 0, 0, 0};
     // work queue: the hub items first, one per pull (they are the long ones); then the other items in chunks of
     // FLAT_CHUNK consecutive list positions per pull, the next item's record and list length in flight while the
     // current one is scored
     constexpr unsigned FLAT_CHUNK = 8;
-    const unsigned n_pulls = nH + (nA + FLAT_CHUNK - 1) / FLAT_CHUNK;
+    const unsigned n_pulls = HUB_ONLY ? nH : nH + (nA + FLAT_CHUNK - 1) / FLAT_CHUNK;   // HUB_ONLY: flat_score_kernel takes the rest
     for (;;) {
         unsigned j = 0;
         if (lane == 0) j = atomicAdd(GG_FCTR(fv, s, 3), 1u);
@@ -759,84 +708,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
         const bool hub_item = j < nH;
         unsigned i = hub_item ? (unsigned)fv.hub[j] : (j - nH) * FLAT_CHUNK;
         const unsigned i_end = hub_item ? i + 1 : ((i + FLAT_CHUNK < nA) ? i + FLAT_CHUNK : nA);
-#if GG_FLAT_SUBWARP
-        if (!hub_item) {
-            // ---- short lists (2..8 candidates: most items beyond step 1), FOUR items at a time, one per 8-lane group.
-            // The canonical sequence on <= 8 candidates only ever combines lanes 0..7 of the 32-lane form with exact zeros
-            // (butterfly sum: x + 0 == x at the xor-16 / xor-8 stages; Kogge-Stone scan: lanes 0..7 take nothing from
-            // offsets 8 and 16, and lane 31 ends as 0 + ... + scan_7), so an 8-lane group reproduces it bit for bit.
-            const int grp = lane >> 3, l8 = lane & 7, gbase = lane & 24;
-            for (unsigned ib = i; ib < i_end; ib += 4) {
-                const unsigned it = ib + (unsigned)grp;
-                const bool have = it < i_end;
-                const int4 rec = have ? A[it] : make_int4(0, 0, 0, 0);
-                const int nrec = have ? fv.item_n[it] : 0;
-                const int n = nrec & 0x3fffffff;
-                const bool small = have && n >= 2 && n <= 8;
-                if (!__any_sync(FULL, small)) continue;
-                const long long w = rec.x;
-                const int cur = small ? rec.y : 0, slot = rec.w;
-                const bool inc_father = (nrec >> 30) & 1;
-                const int *ids = fv.pool_ids + (size_t)it * (size_t)fv.stride;
-                const int my_id = (small && l8 < n) ? ids[l8] : cur;
-                float4 c4[CPL];
-                load_row<CPL>(d.emb, d.ld, cur, l8, c4);
-                const int root = small ? d.roots[slot] : 0;
-                const uint32_t k = small ? (uint32_t)(w - __ldg(d.walk_ptr + slot)) : 0u;
-                const int nmax = __reduce_max_sync(FULL, small ? n : 0);
-                float score = 0.0f;
-                for (int j = 0; j < nmax; j += 2) {
-                    const int ca = __shfl_sync(FULL, my_id, gbase + j), cb = __shfl_sync(FULL, my_id, gbase + j + 1);
-                    const float *ra = d.emb + (size_t)ca * (size_t)d.ld + 4 * l8;
-                    const float *rb = d.emb + (size_t)cb * (size_t)d.ld + 4 * l8;
-                    float4 xa[CPL], xb[CPL];
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) xa[c] = ldg4(ra + 32 * c);
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) xb[c] = ldg4(rb + 32 * c);
-                    const float ba = __ldg(d.bias + ca), bb = __ldg(d.bias + cb);
-                    float sa = 0.0f, sb = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) sa = fma4(c4[c], xa[c], sa);
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) sb = fma4(c4[c], xb[c], sb);
-                    sa = group8_sum(sa);
-                    sb = group8_sum(sb);
-                    if (l8 == j) score = __fadd_rn(sa, ba);
-                    if (l8 == j + 1) score = __fadd_rn(sb, bb);
-                }
-                const bool mine = small && l8 < n;
-                float m = mine ? score : -INFINITY;
-                m = fmaxf(m, __shfl_xor_sync(FULL, m, 4)); m = fmaxf(m, __shfl_xor_sync(FULL, m, 2)); m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
-                const float e = mine ? exp_c(__fsub_rn(score, m)) : 0.0f;
-                const float S = group8_sum(e);                         // == warp_sum_butterfly over (e_0..e_7, 0, ..., 0)
-                double x = (double)__fdiv_rn(e, small ? S : 1.0f);
-#pragma unroll
-                for (int off = 1; off < 8; off <<= 1) {
-                    const double y = __shfl_up_sync(FULL, x, off, 8);
-                    if (l8 >= off) x = __dadd_rn(x, y);
-                }
-                const double total = __shfl_sync(FULL, x, gbase + 7);   // == lane 31 of the 32-lane scan
-                uint32_t a, b;
-                philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
-                const double u = u53(a, b);
-                const unsigned hit = (__ballot_sync(FULL, mine && (__ddiv_rn(x, small ? total : 1.0) > u)) >> gbase) & 0xffu;
-                const int idx = hit ? __ffs(hit) - 1 : n - 1;
-                const int nxt = __shfl_sync(FULL, my_id, gbase + (small ? idx : 0));
-                if (small && l8 == 0) {
-                    flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
-                    raw_steps += 1; raw_suml += (unsigned)n; rows_small += 1u + (unsigned)n;
-                }
-            }
-        }
-#endif
         int4 rec_next = A[i];
         int n_next = hub_item ? 0 : fv.item_n[i];
         for (; i < i_end; ++i) {
             const int4 rec = rec_next;
             const int nrec = n_next;
             if (i + 1 < i_end) { rec_next = A[i + 1]; n_next = fv.item_n[i + 1]; }
-            if (!hub_item && (nrec & 0x3fffffff) < (GG_FLAT_SUBWARP ? 9 : 2)) continue;   // finished by flat_enum_kernel / a hub item / done above
+            if (!hub_item && (nrec & 0x3fffffff) < 2) continue;      // finished by flat_enum_kernel, or a hub item
             const long long w = rec.x;
             const int cur = rec.y, prev = rec.z, slot = rec.w;
             int n, idx, nxt;
@@ -846,7 +724,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
                 inc_father = step_includes_father(d, s, s == 1 ? d.first_edge[w] : 0);
                 const uint32_t *tb = d.tree_bits + (size_t)slot * (size_t)d.tree_words;
                 int *ids; float *sc; float m;
-                build_list<CPL, GG_UNR_HUB>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
+                build_list<CPL, UNR>(d, tb, cur, prev, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
                 if (n == 0) {
                     if (lane == 0) flat_void(d, s, w);
                     continue;
@@ -855,7 +733,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
                 idx = (n == 1) ? 0 : choose_index(sc, n, m, u53(a, b), lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
                 nxt = ids[idx];
                 __syncwarp();
-            } else {
+            } else if (!HUB_ONLY) {
                 n = nrec & 0x3fffffff;
                 inc_father = (nrec >> 30) & 1;
                 const int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
@@ -870,6 +748,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
                 idx = choose_index(s_sc, n, m, u53(a, b), lane);
                 nxt = ids[idx];
                 __syncwarp();
+            } else {
+                continue;
             }
             if (lane == 0) {
                 flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
@@ -877,14 +757,104 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
             }
         }
     }
-    // lane 0 counted the full-warp items, lane 0 of every 8-lane group (lanes 0, 8, 16, 24) its short ones; rows_gathered
-    // (hub and long-list path) is warp-uniform, rows_small per group
-#pragma unroll
-    for (int off = 16; off >= 8; off >>= 1) {
-        raw_steps += __shfl_xor_sync(FULL, raw_steps, off); raw_suml += __shfl_xor_sync(FULL, raw_suml, off);
-        overflow += __shfl_xor_sync(FULL, overflow, off); rows_small += __shfl_xor_sync(FULL, rows_small, off);
+    if (lane == 0) {
+        if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
+        if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
+        if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
+        if (rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
     }
-    rows_gathered += rows_small;
+}
+
+// flat_score_kernel: the items that do NOT stand on a score-cached node, when the level is split in two launches
+// (desc.flat_split): no hub code in the kernel, the walk's own row parked in shared memory instead of 16 registers, so
+// that THREE candidate rows per 8-lane group (12 per warp, 6 KB) are in flight instead of two.
+constexpr int FLAT_SC_CAP = 320;                          // >= the pool stride (hub_threshold < 320)
+#define GG_FLAT_SCORE_SMEM_PER_WARP(C) (gg::FLAT_SC_CAP * 4 + 8 * (C) * 16)
+
+template <int CPL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) flat_score_kernel(const __grid_constant__ gg_walk_desc d, const FlatView fv,
+                                                                           const int s) {
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, grp = lane >> 3, g = lane & 7;
+    float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * (FLAT_SC_CAP * 4 + 8 * CPL * 16));
+    float4 *s_cur = reinterpret_cast<float4 *>(s_sc + FLAT_SC_CAP);
+    const int4 *A = fv.list[s & 1];
+    const unsigned nA = *GG_FCTR(fv, s, 0);
+    const uint32_t k0 = (uint32_t)d.seed, k1 = (uint32_t)(d.seed >> 32);
+    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
+    constexpr unsigned FLAT_CHUNK = 8;
+    const unsigned n_pulls = (nA + FLAT_CHUNK - 1) / FLAT_CHUNK;
+    for (;;) {
+        unsigned j = 0;
+        if (lane == 0) j = atomicAdd(GG_FCTR(fv, s, 2), 1u);
+        j = __shfl_sync(FULL, j, 0);
+        if (j >= n_pulls) break;
+        unsigned i = j * FLAT_CHUNK;
+        const unsigned i_end = (i + FLAT_CHUNK < nA) ? i + FLAT_CHUNK : nA;
+        int4 rec_next = A[i];
+        int n_next = fv.item_n[i];
+        for (; i < i_end; ++i) {
+            const int4 rec = rec_next;
+            const int nrec = n_next;
+            if (i + 1 < i_end) { rec_next = A[i + 1]; n_next = fv.item_n[i + 1]; }
+            const int n = nrec & 0x3fffffff;
+            if (n < 2) continue;                            // finished by flat_enum_kernel, or a hub item
+            const bool inc_father = (nrec >> 30) & 1;
+            const long long w = rec.x;
+            const int cur = rec.y, slot = rec.w;
+            const int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
+            // the walk's own row: one float4 chunk per lane (two at ld = 256), stored to shared memory only AFTER the first
+            // candidate rows have been requested, so that both round trips overlap
+            float4 own[(CPL + 3) / 4];
+#pragma unroll
+            for (int q = 0; q < (CPL + 3) / 4; ++q)
+                own[q] = (lane + 32 * q < 8 * CPL) ? ldg4(d.emb + (size_t)cur * (size_t)d.ld + 4 * (lane + 32 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int root = d.roots[slot];
+            const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
+            for (int i0 = 0; i0 < n; i0 += 12) {
+                int ci[3];
+                float4 x[3][CPL];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { const int t = i0 + 4 * r + grp; ci[r] = (t < n) ? ids[t] : cur; }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float *row = d.emb + (size_t)ci[r] * (size_t)d.ld + 4 * g;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) x[r][c] = ldg4(row + 32 * c);
+                }
+                float bs[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) bs[r] = __ldg(d.bias + ci[r]);
+                if (i0 == 0) {
+#pragma unroll
+                    for (int q = 0; q < (CPL + 3) / 4; ++q)
+                        if (lane + 32 * q < 8 * CPL) s_cur[lane + 32 * q] = own[q];
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) acc = fma4(s_cur[g + 8 * c], x[r][c], acc);   // == score_list's chain (chunk g + 8 c)
+                    acc = group8_sum(acc);
+                    const int t = i0 + 4 * r + grp;
+                    if (g == 0 && t < n) s_sc[t] = __fadd_rn(acc, bs[r]);
+                }
+            }
+            __syncwarp();
+            rows_gathered += 1u + (unsigned)n;
+            const float m = list_max(s_sc, n, lane);
+            uint32_t a, b;
+            philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
+            const int idx = choose_index(s_sc, n, m, u53(a, b), lane);
+            const int nxt = ids[idx];
+            __syncwarp();
+            if (lane == 0) {
+                flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
+                raw_steps += 1; raw_suml += (unsigned)n;
+            }
+        }
+    }
     if (lane == 0) {
         if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
         if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
@@ -1105,6 +1075,7 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
         GG_REQUIRE(!d.walk_order || d.rng_mode == GG_RNG_PHILOX, "walk_order needs GG_RNG_PHILOX");
     }
     GG_REQUIRE(!d.edge_score || (d.hub_threshold > 0 && d.hub_threshold < gg::SMEM_CAP), "hub_threshold out of range");
+    static_assert(gg::FLAT_SC_CAP >= gg::SMEM_CAP, "flat_score_kernel scores a whole pool slab in shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));
     if (d.n_walks == 0 || d.n_roots == 0) return 0;
@@ -1169,9 +1140,16 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
                 GG_CHECK(cudaGetLastError());
                 switch (cpl) {
 #define GG_FLAT(C)                                                                                                    \
-    GG_CHECK(cudaFuncSetAttribute(gg::flat_choose_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                  gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                      \
-    gg::flat_choose_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d, fv, s)
+    if (d.flat_split) {                                                                                              \
+        GG_CHECK(cudaFuncSetAttribute(gg::flat_choose_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                  \
+        gg::flat_choose_kernel<C, true><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d, fv, s); \
+        gg::flat_score_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * GG_FLAT_SCORE_SMEM_PER_WARP(C), st>>>(d, fv, s); \
+    } else {                                                                                                         \
+        GG_CHECK(cudaFuncSetAttribute(gg::flat_choose_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                  \
+        gg::flat_choose_kernel<C, false><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d, fv, s); \
+    }
                     case 1: GG_FLAT(1); break;
                     case 2: GG_FLAT(2); break;
                     case 4: GG_FLAT(4); break;

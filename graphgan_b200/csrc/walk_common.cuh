@@ -18,15 +18,6 @@ namespace gg {
 #ifndef GG_UNR_S1
 #define GG_UNR_S1 8
 #endif
-#ifndef GG_UNR_HUB
-#define GG_UNR_HUB GG_UNR     // bitmap words in flight when flat_choose_kernel enumerates a cached (hub) list
-#endif
-#ifndef GG_FLAT_SUBWARP
-#define GG_FLAT_SUBWARP 0     // flat_choose_kernel: lists of 2..8 candidates four at a time, one per 8-lane group (A/B)
-#endif
-#ifndef GG_ENUM_TWO_PHASE
-#define GG_ENUM_TWO_PHASE 0   // cached lists below the TMA-staging size: entry numbers first, then ids + scores (A/B)
-#endif
 #ifndef GG_WALK_MIN_CTAS
 #define GG_WALK_MIN_CTAS 4
 #endif
