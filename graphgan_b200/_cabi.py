@@ -34,7 +34,7 @@ class WalkDesc(C.Structure):
         ("hub_threshold", C.c_int32), ("no_tma", C.c_int32), ("walk_slot", C.c_void_p),
         ("s1_nq", C.c_int64), ("s1_slot", C.c_void_p), ("s1_ptr", C.c_void_p), ("s1_cnt", C.c_void_p), ("s1_n", C.c_void_p),
         ("s1_q", C.c_void_p), ("s1_ids", C.c_void_p), ("first_idx", C.c_void_p), ("s1_order", C.c_void_p), ("walk_order", C.c_void_p),
-        ("flat_buf", C.c_void_p), ("flat_bytes", C.c_int64), ("flat_steps", C.c_int32), ("flat_split", C.c_int32),
+        ("flat_buf", C.c_void_p), ("flat_bytes", C.c_int64), ("flat_steps", C.c_int32), ("flat_reserved", C.c_int32),
     ]
 
 

@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(FLAT_ENUM_WARPS * 32, 6) flat_enum_kernel(cons
     }
 }
 
-template <int CPL, bool HUB_ONLY>
+template <int CPL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose_kernel(const __grid_constant__ gg_walk_desc d,
                                                                                         const FlatView fv, const int s) {
     extern __shared__ __align__(16) unsigned char walk_smem[];
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
     // FLAT_CHUNK consecutive list positions per pull, the next item's record and list length in flight while the
     // current one is scored
     constexpr unsigned FLAT_CHUNK = 8;
-    const unsigned n_pulls = HUB_ONLY ? nH : nH + (nA + FLAT_CHUNK - 1) / FLAT_CHUNK;   // HUB_ONLY: flat_score_kernel takes the rest
+    const unsigned n_pulls = nH + (nA + FLAT_CHUNK - 1) / FLAT_CHUNK;
     for (;;) {
         unsigned j = 0;
         if (lane == 0) j = atomicAdd(GG_FCTR(fv, s, 3), 1u);
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
                 idx = (n == 1) ? 0 : choose_index(sc, n, m, u53(a, b), lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
                 nxt = ids[idx];
                 __syncwarp();
-            } else if (!HUB_ONLY) {
+            } else {
                 n = nrec & 0x3fffffff;
                 inc_father = (nrec >> 30) & 1;
                 const int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
@@ -748,107 +748,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) flat_choose
                 idx = choose_index(s_sc, n, m, u53(a, b), lane);
                 nxt = ids[idx];
                 __syncwarp();
-            } else {
-                continue;
             }
-            if (lane == 0) {
-                flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
-                raw_steps += 1; raw_suml += (unsigned)n;
-            }
-        }
-    }
-    if (lane == 0) {
-        if (raw_steps) atomicAdd(d.counters + GG_CNT_RAW_STEPS, raw_steps);
-        if (raw_suml) atomicAdd(d.counters + GG_CNT_RAW_SUML, raw_suml);
-        if (overflow) atomicAdd(d.counters + GG_CNT_PATH_OVERFLOW, overflow);
-        if (rows_gathered) atomicAdd(d.counters + GG_CNT_ROWS_GATHERED, rows_gathered);
-    }
-}
-
-// flat_score_kernel: the items that do NOT stand on a score-cached node, when the level is split in two launches
-// (desc.flat_split): no hub code in the kernel, the walk's own row parked in shared memory instead of 16 registers, so
-// that THREE candidate rows per 8-lane group (12 per warp, 6 KB) are in flight instead of two.
-constexpr int FLAT_SC_CAP = 320;                          // >= the pool stride (hub_threshold < 320)
-#define GG_FLAT_SCORE_SMEM_PER_WARP(C) (gg::FLAT_SC_CAP * 4 + 8 * (C) * 16)
-
-template <int CPL>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) flat_score_kernel(const __grid_constant__ gg_walk_desc d, const FlatView fv,
-                                                                           const int s) {
-    extern __shared__ __align__(16) unsigned char walk_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, grp = lane >> 3, g = lane & 7;
-    float *s_sc = reinterpret_cast<float *>(walk_smem + (size_t)wid * (FLAT_SC_CAP * 4 + 8 * CPL * 16));
-    float4 *s_cur = reinterpret_cast<float4 *>(s_sc + FLAT_SC_CAP);
-    const int4 *A = fv.list[s & 1];
-    const unsigned nA = *GG_FCTR(fv, s, 0);
-    const uint32_t k0 = (uint32_t)d.seed, k1 = (uint32_t)(d.seed >> 32);
-    unsigned long long raw_steps = 0, raw_suml = 0, overflow = 0, rows_gathered = 0;
-    constexpr unsigned FLAT_CHUNK = 8;
-    const unsigned n_pulls = (nA + FLAT_CHUNK - 1) / FLAT_CHUNK;
-    for (;;) {
-        unsigned j = 0;
-        if (lane == 0) j = atomicAdd(GG_FCTR(fv, s, 2), 1u);
-        j = __shfl_sync(FULL, j, 0);
-        if (j >= n_pulls) break;
-        unsigned i = j * FLAT_CHUNK;
-        const unsigned i_end = (i + FLAT_CHUNK < nA) ? i + FLAT_CHUNK : nA;
-        int4 rec_next = A[i];
-        int n_next = fv.item_n[i];
-        for (; i < i_end; ++i) {
-            const int4 rec = rec_next;
-            const int nrec = n_next;
-            if (i + 1 < i_end) { rec_next = A[i + 1]; n_next = fv.item_n[i + 1]; }
-            const int n = nrec & 0x3fffffff;
-            if (n < 2) continue;                            // finished by flat_enum_kernel, or a hub item
-            const bool inc_father = (nrec >> 30) & 1;
-            const long long w = rec.x;
-            const int cur = rec.y, slot = rec.w;
-            const int *ids = fv.pool_ids + (size_t)i * (size_t)fv.stride;
-            // the walk's own row: one float4 chunk per lane (two at ld = 256), stored to shared memory only AFTER the first
-            // candidate rows have been requested, so that both round trips overlap
-            float4 own[(CPL + 3) / 4];
-#pragma unroll
-            for (int q = 0; q < (CPL + 3) / 4; ++q)
-                own[q] = (lane + 32 * q < 8 * CPL) ? ldg4(d.emb + (size_t)cur * (size_t)d.ld + 4 * (lane + 32 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const int root = d.roots[slot];
-            const uint32_t k = (uint32_t)(w - __ldg(d.walk_ptr + slot));
-            for (int i0 = 0; i0 < n; i0 += 12) {
-                int ci[3];
-                float4 x[3][CPL];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) { const int t = i0 + 4 * r + grp; ci[r] = (t < n) ? ids[t] : cur; }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const float *row = d.emb + (size_t)ci[r] * (size_t)d.ld + 4 * g;
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) x[r][c] = ldg4(row + 32 * c);
-                }
-                float bs[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) bs[r] = __ldg(d.bias + ci[r]);
-                if (i0 == 0) {
-#pragma unroll
-                    for (int q = 0; q < (CPL + 3) / 4; ++q)
-                        if (lane + 32 * q < 8 * CPL) s_cur[lane + 32 * q] = own[q];
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) acc = fma4(s_cur[g + 8 * c], x[r][c], acc);   // == score_list's chain (chunk g + 8 c)
-                    acc = group8_sum(acc);
-                    const int t = i0 + 4 * r + grp;
-                    if (g == 0 && t < n) s_sc[t] = __fadd_rn(acc, bs[r]);
-                }
-            }
-            __syncwarp();
-            rows_gathered += 1u + (unsigned)n;
-            const float m = list_max(s_sc, n, lane);
-            uint32_t a, b;
-            philox4x32_10((uint32_t)root, k, (uint32_t)s, d.pass_tag, k0, k1, a, b);
-            const int idx = choose_index(s_sc, n, m, u53(a, b), lane);
-            const int nxt = ids[idx];
-            __syncwarp();
             if (lane == 0) {
                 flat_advance(d, fv, s, w, slot, cur, n, idx, nxt, inc_father, overflow);
                 raw_steps += 1; raw_suml += (unsigned)n;
@@ -1075,7 +975,6 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
         GG_REQUIRE(!d.walk_order || d.rng_mode == GG_RNG_PHILOX, "walk_order needs GG_RNG_PHILOX");
     }
     GG_REQUIRE(!d.edge_score || (d.hub_threshold > 0 && d.hub_threshold < gg::SMEM_CAP), "hub_threshold out of range");
-    static_assert(gg::FLAT_SC_CAP >= gg::SMEM_CAP, "flat_score_kernel scores a whole pool slab in shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     GG_CHECK(cudaMemsetAsync(d.work_counter, 0, sizeof(unsigned int), st));
     if (d.n_walks == 0 || d.n_roots == 0) return 0;
@@ -1140,16 +1039,9 @@ extern "C" int gg_walk_sample(const gg_walk_desc *dp, void *stream) {
                 GG_CHECK(cudaGetLastError());
                 switch (cpl) {
 #define GG_FLAT(C)                                                                                                    \
-    if (d.flat_split) {                                                                                              \
-        GG_CHECK(cudaFuncSetAttribute(gg::flat_choose_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                      gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                  \
-        gg::flat_choose_kernel<C, true><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d, fv, s); \
-        gg::flat_score_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * GG_FLAT_SCORE_SMEM_PER_WARP(C), st>>>(d, fv, s); \
-    } else {                                                                                                         \
-        GG_CHECK(cudaFuncSetAttribute(gg::flat_choose_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                  \
-        gg::flat_choose_kernel<C, false><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d, fv, s); \
-    }
+    GG_CHECK(cudaFuncSetAttribute(gg::flat_choose_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                  gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP));                                      \
+    gg::flat_choose_kernel<C><<<ctas, gg::WARPS_PER_CTA * 32, gg::WARPS_PER_CTA * gg::WALK_SMEM_PER_WARP, st>>>(d, fv, s)
                     case 1: GG_FLAT(1); break;
                     case 2: GG_FLAT(2); break;
                     case 4: GG_FLAT(4); break;

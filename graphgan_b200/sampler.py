@@ -199,7 +199,6 @@ class WalkSampler:
         self.bfs_flags = 0
         # level-synchronous walk steps (csrc/walk.cu: flat_*_kernel) for steps 1..flat_steps; 0 = persistent kernel only
         self.flat_steps = int(os.environ.get("GG_FLAT_STEPS", "4"))
-        self.flat_split = int(os.environ.get("GG_FLAT_SPLIT", "0"))   # 1: hub items and the others in separate launches per step
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -261,7 +260,7 @@ class WalkSampler:
                     d.s1_order = ptr(b["order"])
                 if self.flat_steps > 0:
                     buf = plan.flat_buffer(self)
-                    d.flat_buf, d.flat_bytes, d.flat_steps, d.flat_split = ptr(buf), buf.numel(), self.flat_steps, self.flat_split
+                    d.flat_buf, d.flat_bytes, d.flat_steps = ptr(buf), buf.numel(), self.flat_steps
         return d
 
     def precompute(self, emb, bias, plan, desc=None):

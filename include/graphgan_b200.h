@@ -133,8 +133,7 @@ typedef struct gg_walk_desc {
     void *flat_buf;             /* device scratch of gg_walk_flat_bytes(n_walks, hub_threshold, flat_steps) bytes */
     int64_t flat_bytes;
     int32_t flat_steps;         /* 0 = off (persistent kernel only); <= 14 */
-    int32_t flat_split;         /* 1 = two launches per step: the walks on score-cached nodes (long lists), then the others
-                                   in a kernel of their own (three candidate rows per 8-lane group in flight); identical results */
+    int32_t flat_reserved;
 } gg_walk_desc;
 
 /* all_score[u, v] = e_u.e_v + b_v (generator.py:21) for every walk-CSR entry (u -> v) of the listed hub
