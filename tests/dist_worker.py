@@ -126,7 +126,9 @@ def main(mode):
     from tests.golden import loader
     import tempfile
     c = loader.load("rand1200")
-    tmp = tempfile.mkdtemp()
+    box = [tempfile.mkdtemp() if rank == 0 else None]       # ONE directory for all ranks: the checkpoint is written by rank 0
+    dist.broadcast_object_list(box, src=0)                   # and read by every rank (part 4)
+    tmp = box[0]
     config.n_emb, config.n_epochs, config.n_epochs_dis, config.dis_interval = 50, 1, 1, 1
     config.n_epochs_gen, config.gen_interval, config.n_sample_gen, config.seed = 1, 1, 2, 9
     config.app = "none"
