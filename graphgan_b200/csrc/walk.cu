@@ -198,9 +198,6 @@ __device__ __forceinline__ void build_list(const gg_walk_desc &d, const uint32_t
 #define GG_S1_MIN_WALKS 1
 #endif
 constexpr int S1_MIN_WALKS = GG_S1_MIN_WALKS;
-#ifndef GG_S1_DIRECT
-#define GG_S1_DIRECT 1    // a pair picked by exactly ONE walk: step1_cdf_kernel draws for that walk itself (no CDF array)
-#endif
 
 // Does the pair (root slot, i-th neighbour) at `s1pos` get a shared CDF from step1_cdf_kernel?  With S1_MIN_WALKS = 1: every
 // pair that was picked (measured: hub lists are long and the builder's queue starts the longest first; 2 -- pairs picked
@@ -264,12 +261,8 @@ __device__ __forceinline__ int walk_one(const gg_walk_desc &d, Rng &rng, int slo
             inc_father = !d.for_d && !((d.d1_bits[fedge >> 5] >> (fedge & 31)) & 1u);
             const double u = rng.draw((uint32_t)root, k, 1u);
             const long long o = __ldg(d.s1_ptr + s1pos);
-            if (GG_S1_DIRECT && __ldg(d.s1_cnt + s1pos) == 1) {      // drawn by step1_cdf_kernel: [next node, chosen index]
-                nxt = d.s1_ids[o]; idx = d.s1_ids[o + 1];
-            } else {
-                idx = (n == 1) ? 0 : cdf_search_raw(d.s1_q + o, n, u);
-                nxt = __ldg(d.s1_ids + o + idx);
-            }
+            idx = (n == 1) ? 0 : cdf_search_raw(d.s1_q + o, n, u);
+            nxt = __ldg(d.s1_ids + o + idx);
         } else {
             // ---- candidate list (graph_gan.py:250-259) + scores
             inc_father = step > 0;
@@ -335,9 +328,6 @@ __global__ void root_step_kernel(const __grid_constant__ gg_walk_desc d) {
     const int idx = cdf_search(d.root_q + o, n, u53(a, b));
     d.first_idx[w] = idx;
     atomicAdd(d.s1_cnt + o + idx, 1);
-#if GG_S1_DIRECT
-    d.s1_n[o + idx] = (int)w;        // (scratch until step1_cdf_kernel writes the list length: THE walk of a pair picked once)
-#endif
 }
 
 constexpr int S1_SINGLES = 8192, S1_CHUNK = 16;
@@ -398,33 +388,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, WALK_MIN_CTAS) step1_cdf_k
         const int c = __ldg(d.adj + e);
         const bool inc_father = !d.for_d && !((d.d1_bits[e >> 5] >> (e & 31)) & 1u);   // graph_gan.py:258-259
         int n; float m; int *ids; float *sc;
-#if GG_S1_DIRECT
-        const bool single = __ldg(d.s1_cnt + pos) == 1;
-        const long long w1 = single ? (long long)d.s1_n[pos] : 0;     // read before the slot becomes the list length
-        __syncwarp();
-#endif
         build_list<CPL, UNR_S1>(d, tb, c, root, inc_father, s_ids, s_sc, g_ids, g_sc, lane, n, m, ids, sc, rows_gathered, cyc, stg);
         if (lane == 0) d.s1_n[pos] = n;
         if (n == 0) continue;
         const long long o = __ldg(d.s1_ptr + pos);
-#if GG_S1_DIRECT
-        if (single) {
-            // one walk picked this pair: its draw happens here (same Philox counter (root, walk, step 1) and the same
-            // canonical choose as inside a walk); the slice only carries the result: [next node, chosen index].  No CDF
-            // array is written (16 bytes per candidate) and the walk has nothing to search.
-            int idx = 0;
-            if (n > 1) {
-                uint32_t a, b;
-                philox4x32_10((uint32_t)root, (uint32_t)(w1 - __ldg(d.walk_ptr + slot)), 1u, d.pass_tag, (uint32_t)d.seed,
-                              (uint32_t)(d.seed >> 32), a, b);
-                idx = choose_index(sc, n, m, u53(a, b), lane, sc != s_sc ? reinterpret_cast<double *>(s_sc) : nullptr);
-            }
-            const int nxt = ids[idx];
-            __syncwarp();
-            if (lane == 0) { d.s1_ids[o] = nxt; d.s1_ids[o + 1] = idx; }
-            continue;
-        }
-#endif
         for (int i = lane; i < n; i += 32) d.s1_ids[o + i] = ids[i];
         if (n > 1) cdf_store_raw<UNR_S1>(sc, n, m, d.s1_q + o, lane);
         __syncwarp();
@@ -612,15 +579,10 @@ __global__ void __launch_bounds__(256) flat_start_kernel(const __grid_constant__
                     } else {
                         const bool inc_father = step_includes_father(d, 1, fedge);
                         const long long o = __ldg(d.s1_ptr + s1pos);
-                        int idx, nxt;
-                        if (GG_S1_DIRECT && __ldg(d.s1_cnt + s1pos) == 1) {   // drawn by step1_cdf_kernel
-                            nxt = d.s1_ids[o]; idx = d.s1_ids[o + 1];
-                        } else {
-                            uint32_t a, b;
-                            philox4x32_10((uint32_t)root, k, 1u, d.pass_tag, (uint32_t)d.seed, (uint32_t)(d.seed >> 32), a, b);
-                            idx = (n == 1) ? 0 : cdf_search_raw(d.s1_q + o, n, u53(a, b));
-                            nxt = __ldg(d.s1_ids + o + idx);
-                        }
+                        uint32_t a, b;
+                        philox4x32_10((uint32_t)root, k, 1u, d.pass_tag, (uint32_t)d.seed, (uint32_t)(d.seed >> 32), a, b);
+                        const int idx = (n == 1) ? 0 : cdf_search_raw(d.s1_q + o, n, u53(a, b));
+                        const int nxt = __ldg(d.s1_ids + o + idx);
                         if (prow && 2 < d.max_path) prow[2] = nxt;
                         ws = 2; wl = n0 + n; steps = 2; suml = (unsigned)(n0 + n);
                         if (inc_father && idx == 0) {
