@@ -41,6 +41,12 @@ def test_cabi_argument_errors_do_not_abort():
     assert lib.gg_pair_grad(7, 1, 0, None, None, None, None, None, 32, C.c_float(0), None, None, None, None, None, None) != 0
     with pytest.raises(_cabi.GGError):
         _cabi.check(lib.gg_bfs_build(10, 20, None, None, 1, None, None, 2, None, 0, None), "gg_bfs_build")
+    with pytest.raises(_cabi.GGError):
+        _cabi.check(lib.gg_bfs_build_ex(10, 20, None, None, None, 1, None, None, 2, None, 0, C.c_float(-1.0), 0, None), "gg_bfs_build_ex")
+    assert lib.gg_reverse_entries(10, 20, None, None, None, None, None) != 0
+    # scratch of the level-synchronous steps: a pure host-side size computation (no GPU): list records + id slabs
+    assert lib.gg_walk_flat_bytes(1000, 128, 4, C.byref(n)) == 0 and n.value >= 1000 * (3 * 16 + 2 * 4 + 128 * 4)
+    assert lib.gg_walk_flat_bytes(1000, 0, 4, C.byref(n)) != 0 and lib.gg_walk_flat_bytes(1000, 128, 99, C.byref(n)) != 0
 
 
 def test_product_does_not_import_oracle():
